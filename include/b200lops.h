@@ -1,0 +1,158 @@
+/* b200lops.h -- C ABI of libb200lops.so
+ *
+ * B200-native (sm_100a) kernels + NCCL collectives for the pylops-mpi
+ * distributed matvec/rmatvec hot path.  Plain pointers and sizes only: every
+ * buffer is a raw DEVICE pointer owned by the caller (unless a parameter is
+ * explicitly named *_host), every stream is a cudaStream_t passed as void*.
+ * Every entry point returns 0 on success, a cudaError_t (1..999) on a CUDA
+ * failure, 1000+ncclResult_t on an NCCL failure, or a B2_ERR_* code; none
+ * throws, none frees or retains caller memory past the call (handles such as
+ * b2_ctx / b2_comm own their private workspaces and have *_destroy).
+ *
+ * Each declaration cites the reference interface (file:line relative to
+ * pylops_mpi/ of PyLops/pylops-mpi @ fb5b7d4) it replaces.
+ */
+#ifndef B200LOPS_H
+#define B200LOPS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_VERSION 100
+
+/* element types */
+enum { B2_F32 = 0, B2_F64 = 1, B2_C64 = 2, B2_C128 = 3, B2_BF16 = 4, B2_I64 = 5 };
+/* reduction operators (mpi4py MPI.SUM / MPI.MAX / MPI.MIN, utils/_nccl.py:23-43) */
+enum { B2_SUM = 0, B2_MAX = 1, B2_MIN = 2 };
+/* local part of DistributedArray._compute_vector_norm, DistributedArray.py:688-758 */
+enum { B2_NRM_COUNT_NONZERO = 0, B2_NRM_SUM_ABS = 1, B2_NRM_SUM_SQ = 2,
+       B2_NRM_MAX_ABS = 3, B2_NRM_MIN_ABS = 4, B2_NRM_SUM_POW = 5 };
+/* MPIFirstDerivative kinds, basicoperators/FirstDerivative.py:104-127 */
+enum { B2_FD_FORWARD = 0, B2_FD_BACKWARD = 1, B2_FD_CENTERED = 2 };
+/* op(A) for gemv/gemm */
+enum { B2_OP_N = 0, B2_OP_T = 1, B2_OP_H = 2 };
+
+/* error codes >= 2000 are library-level */
+enum { B2_OK = 0, B2_ERR_DTYPE = 2001, B2_ERR_ARG = 2002, B2_ERR_HALO = 2003,
+       B2_ERR_WORKSPACE = 2004, B2_ERR_UNSUPPORTED = 2005, B2_ERR_ALIGN = 2006 };
+
+typedef struct b2_ctx b2_ctx;    /* per-device context: SM count, reduction workspace */
+typedef struct b2_comm b2_comm;  /* one NCCL communicator (world, mask group, grid row / col) */
+typedef struct b2_gemm_plan b2_gemm_plan;
+
+int b2_version(void);
+const char* b2_strerror(int code);
+
+/* ---- context --------------------------------------------------------- */
+int b2_ctx_create(int device, b2_ctx** out);
+int b2_ctx_destroy(b2_ctx* ctx);
+int b2_ctx_sm_count(const b2_ctx* ctx, int* out);
+
+/* ---- element-wise (DistributedArray.py:574-652, 809-837: add, iadd,
+ *      multiply, __neg__, conj, copy, zeros_like) ------------------------- */
+/* out = a * op(x) + b * y ; a,b are (re,im) host pairs; y may be NULL (b ignored);
+ * op = conj when conj_x != 0.  out may alias x or y. */
+int b2_lincomb(b2_ctx* ctx, void* out, const double a[2], const void* x, const double b[2],
+               const void* y, size_t n, int dtype, int conj_x, void* stream);
+/* Same with DEVICE-resident real scalars: a = a_scale * (*a_dev) (a_dev may be NULL -> 1),
+ * b likewise; lets a solver iteration run with no host round-trip
+ * (optimization/cls_basic.py:389-397 does five .item() syncs per iteration). */
+int b2_lincomb_dev(b2_ctx* ctx, void* out, const double* a_dev, double a_scale, const void* x,
+                   const double* b_dev, double b_scale, const void* y, size_t n, int dtype,
+                   void* stream);
+/* out = op(x) * y element-wise (DistributedArray.multiply, :630-652) */
+int b2_mul(b2_ctx* ctx, void* out, const void* x, const void* y, size_t n, int dtype,
+           int conj_x, void* stream);
+int b2_fill(b2_ctx* ctx, void* out, const double v[2], size_t n, int dtype, void* stream);
+
+/* ---- local reductions (the per-rank half of DistributedArray.dot :654-686
+ *      and _compute_vector_norm :688-758); results are float64 in DEVICE
+ *      memory, accumulated in float64 in a fixed (deterministic) order ----- */
+/* out_dev[0..1] = sum_i op(x_i) * y_i  (re, im); op = conj when conj_x (numpy.vdot) */
+int b2_dot(b2_ctx* ctx, const void* x, const void* y, size_t n, int dtype, int conj_x,
+           double* out_dev, void* stream);
+/* out_dev[0] = local partial for the requested norm kind (p only for SUM_POW) */
+int b2_norm_partial(b2_ctx* ctx, const void* x, size_t n, int dtype, int kind, double p,
+                    double* out_dev, void* stream);
+/* k dot products <x_j, y_j> in ONE launch: out_dev[0..k) for real dtypes, out_dev[0..2k) as
+ * (re, im) pairs for complex dtypes (CGLS needs q.q and c.c
+ * together, r.r / s.s / x.x together -- cls_basic.py:389, 394-401) */
+int b2_dot_multi(b2_ctx* ctx, int k, const void* const* xs, const void* const* ys, size_t n,
+                 int dtype, int conj_x, double* out_dev, void* stream);
+
+/* ---- MPIFirstDerivative per-rank apply (FirstDerivative.py:129-319) -------
+ * x,y: this rank's row block [nrows_local x ncols] (C order) of the global
+ * [nrows_global x ncols] array, global row offset row0.  halo_lo holds the n_lo
+ * rows immediately before row0, halo_hi the n_hi rows immediately after the
+ * block (the add_ghost_cells payload, DistributedArray.py:876-953); NULL / 0
+ * at the global edges.  Complex arrays: pass the real dtype and 2*ncols. */
+int b2_first_derivative(b2_ctx* ctx, const void* x, void* y, const void* halo_lo, int n_lo,
+                        const void* halo_hi, int n_hi, size_t nrows_local, size_t ncols,
+                        size_t row0, size_t nrows_global, int kind, int order, int edge,
+                        double sampling, int adjoint, int dtype, void* stream);
+/* rows of halo each side needs (1 or 2) */
+int b2_first_derivative_halo(int kind, int order, int adjoint, int* need_lo, int* need_hi);
+/* Same operator on HOST buffers (pageable or pinned).  x_host / y_host address the
+ * GLOBAL [nrows_global x ncols] arrays (to_dist keeps the global array replicated on
+ * every rank's host, DistributedArray.py:440-459); this call processes rows
+ * [row_begin, row_end) and only touches rows [row_begin-2, row_end+2) of x_host and
+ * [row_begin, row_end) of y_host.  Row chunks go through the device with H2D /
+ * kernel / D2H overlapped on three streams.  This is the host-buffer plugin entry
+ * the end-to-end benchmark times. */
+int b2_first_derivative_host(b2_ctx* ctx, const void* x_host, void* y_host, size_t nrows_global,
+                             size_t ncols, size_t row_begin, size_t row_end, int kind, int order,
+                             int edge, double sampling, int adjoint, int dtype);
+
+/* ---- dense per-rank matvec (the pylops.MatrixMult block inside MPIBlockDiag /
+ *      MPIVStack, BlockDiag.py:127-129,139-141; VStack.py:129-131,144-145; and
+ *      the M==1 tile product of MPIMatrixMult, MatrixMult.py:366-370,670) ----
+ * y[m or n] = op(A[m x n, row-major, leading dim lda]) x ; dtype_a in
+ * {F32,F64,C64,C128,BF16}; x,y have dtype_xy (BF16 A pairs with F32 x/y). */
+int b2_gemv(b2_ctx* ctx, const void* A, size_t lda, size_t m, size_t n, const void* x, void* y,
+            int op, int dtype_a, int dtype_xy, void* stream);
+
+/* ---- dense tile product on tcgen05 tensor cores (MPIMatrixMult with M>1,
+ *      MatrixMult.py:663-670, 742-763): C[m x n] (+)= op(A) B, A,B bf16,
+ *      C fp32, all row-major ------------------------------------------------ */
+int b2_gemm_bf16(b2_ctx* ctx, const void* A, size_t lda, const void* B, size_t ldb, float* C,
+                 size_t ldc, size_t m, size_t n, size_t k, int op_a, int accumulate,
+                 void* stream);
+/* generic SIMT tile product for the dtypes tensor cores do not serve
+ * (f32/f64/c64/c128 parity cases of tests/test_matrixmult.py) */
+int b2_gemm(b2_ctx* ctx, const void* A, size_t lda, const void* B, size_t ldb, void* C, size_t ldc,
+            size_t m, size_t n, size_t k, int op_a, int accumulate, int dtype, void* stream);
+
+/* ---- MPIFredholm1 per-rank batched product (Fredholm1.py:119-129, 147-167):
+ *      y[s] = op(G[s]) x[s] for s < nsl ; G[s] is nx x ny, x[s] is (ny|nx) x nz */
+int b2_batched_gemm(b2_ctx* ctx, const void* G, const void* x, void* y, size_t nsl, size_t nx,
+                    size_t ny, size_t nz, int adjoint, int dtype, void* stream);
+
+/* ---- NCCL collectives (utils/_nccl.py:98-403, utils/_mpi.py:21-344,
+ *      Distributed.py:35-349) --------------------------------------------- */
+int b2_get_unique_id(void* id128_host);                       /* _nccl.py:98-132 */
+int b2_comm_create(int rank, int size, const void* id128_host, int device, b2_comm** out);
+int b2_comm_split(b2_comm* comm, int color, int key, b2_comm** out);   /* _nccl.py:135-165 */
+int b2_comm_destroy(b2_comm* comm);
+int b2_comm_rank(const b2_comm* comm, int* rank, int* size);
+int b2_allreduce(b2_comm* comm, const void* send, void* recv, size_t n, int dtype, int op,
+                 void* stream);                               /* _nccl.py:203-240 */
+int b2_allgather(b2_comm* comm, const void* send, void* recv, size_t n_per_rank, int dtype,
+                 void* stream);                               /* _nccl.py:167-200 */
+/* uneven gather without the reference's pad-to-max (_nccl.py:363-403): rank r
+ * contributes counts[r] elements; recv is the plain concatenation */
+int b2_allgatherv(b2_comm* comm, const void* send, void* recv, const size_t* counts_host,
+                  int dtype, void* stream);
+int b2_bcast(b2_comm* comm, void* buf, size_t n, int dtype, int root, void* stream);  /* :243-262 */
+int b2_send(b2_comm* comm, const void* buf, size_t n, int dtype, int peer, void* stream); /* :265-286 */
+int b2_recv(b2_comm* comm, void* buf, size_t n, int dtype, int peer, void* stream);       /* :289-316 */
+int b2_group_start(void);
+int b2_group_end(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LOPS_H */

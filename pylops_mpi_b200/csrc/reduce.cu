@@ -1,0 +1,422 @@
+// Local (per-rank) reductions behind DistributedArray.dot / norm
+// (reference: pylops_mpi/DistributedArray.py:654-686, 688-758).
+//
+// One launch per reduction: every CTA streams its grid-stride share with
+// 16-byte loads, accumulates in float64 registers, reduces with warp shuffles,
+// writes one partial per CTA; the last CTA to finish (ticket counter) folds the
+// partials in CTA order, so the result is deterministic for a given n.
+// HBM-bound: algorithmic bytes = n*sizeof(T) per operand.
+#include <math.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int RED_THREADS = 256;
+constexpr int RED_UNROLL = 4;
+enum { MODE_SUM = 0, MODE_MAX = 1, MODE_MIN = 2 };
+
+template <int MODE>
+__device__ __forceinline__ double comb(double a, double b) {
+  if (MODE == MODE_SUM) return a + b;
+  if (MODE == MODE_MAX) return fmax(a, b);
+  return fmin(a, b);
+}
+template <int MODE>
+__device__ __forceinline__ double ident() {
+  if (MODE == MODE_SUM) return 0.0;
+  if (MODE == MODE_MAX) return 0.0;  // all candidates are |x| >= 0
+  return INFINITY;
+}
+template <int MODE>
+__device__ __forceinline__ double warp_comb(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = comb<MODE>(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- functors --------------------------------------------------------------
+// real(acc, x, y) consumes one real element; cx(acc, xr, xi, yr, yi) one complex.
+template <bool CONJ>
+struct DotF {
+  static constexpr int NOUT_REAL = 1, NOUT_CX = 2, MODE = MODE_SUM;
+  static constexpr bool HAS_Y = true;
+  double p;
+  template <typename T>
+  __device__ __forceinline__ void real(double* acc, T x, T y) const {
+    acc[0] = fma((double)x, (double)y, acc[0]);
+  }
+  template <typename T>
+  __device__ __forceinline__ void cx(double* acc, T xr, T xi, T yr, T yi) const {
+    double a = xr, b = CONJ ? -(double)xi : (double)xi, c = yr, d = yi;
+    acc[0] += a * c - b * d;
+    acc[1] += a * d + b * c;
+  }
+};
+struct SumSqF {
+  static constexpr int NOUT_REAL = 1, NOUT_CX = 1, MODE = MODE_SUM;
+  static constexpr bool HAS_Y = false;
+  double p;
+  template <typename T>
+  __device__ __forceinline__ void real(double* acc, T x, T) const {
+    acc[0] = fma((double)x, (double)x, acc[0]);
+  }
+  template <typename T>
+  __device__ __forceinline__ void cx(double* acc, T xr, T xi, T, T) const {
+    acc[0] += (double)xr * (double)xr + (double)xi * (double)xi;
+  }
+};
+struct SumAbsF {
+  static constexpr int NOUT_REAL = 1, NOUT_CX = 1, MODE = MODE_SUM;
+  static constexpr bool HAS_Y = false;
+  double p;
+  template <typename T>
+  __device__ __forceinline__ void real(double* acc, T x, T) const { acc[0] += fabs((double)x); }
+  template <typename T>
+  __device__ __forceinline__ void cx(double* acc, T xr, T xi, T, T) const {
+    acc[0] += hypot((double)xr, (double)xi);
+  }
+};
+struct CountNzF {
+  static constexpr int NOUT_REAL = 1, NOUT_CX = 1, MODE = MODE_SUM;
+  static constexpr bool HAS_Y = false;
+  double p;
+  template <typename T>
+  __device__ __forceinline__ void real(double* acc, T x, T) const { acc[0] += (x != (T)0) ? 1.0 : 0.0; }
+  template <typename T>
+  __device__ __forceinline__ void cx(double* acc, T xr, T xi, T, T) const {
+    acc[0] += (xr != (T)0 || xi != (T)0) ? 1.0 : 0.0;
+  }
+};
+template <int M>
+struct ExtAbsF {
+  static constexpr int NOUT_REAL = 1, NOUT_CX = 1, MODE = M;
+  static constexpr bool HAS_Y = false;
+  double p;
+  template <typename T>
+  __device__ __forceinline__ void real(double* acc, T x, T) const { acc[0] = comb<M>(acc[0], fabs((double)x)); }
+  template <typename T>
+  __device__ __forceinline__ void cx(double* acc, T xr, T xi, T, T) const {
+    acc[0] = comb<M>(acc[0], hypot((double)xr, (double)xi));
+  }
+};
+struct SumPowF {
+  static constexpr int NOUT_REAL = 1, NOUT_CX = 1, MODE = MODE_SUM;
+  static constexpr bool HAS_Y = false;
+  double p;
+  template <typename T>
+  __device__ __forceinline__ void real(double* acc, T x, T) const { acc[0] += pow(fabs((double)x), p); }
+  template <typename T>
+  __device__ __forceinline__ void cx(double* acc, T xr, T xi, T, T) const {
+    acc[0] += pow(hypot((double)xr, (double)xi), p);
+  }
+};
+
+template <typename T, bool CX, typename F>
+__device__ __forceinline__ void consume_vec(const F& f, double* acc, const Vec16<T>& vx,
+                                            const Vec16<T>& vy) {
+  constexpr int V = Vec16<T>::N;
+  if (!CX) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) f.real(acc, vx.v[k], vy.v[k]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < V; k += 2) f.cx(acc, vx.v[k], vx.v[k + 1], vy.v[k], vy.v[k + 1]);
+  }
+}
+
+// n_real = number of T scalars (2 per complex element).  VEC path requires 16B alignment.
+template <typename T, bool CX, bool VEC, typename F>
+__global__ void __launch_bounds__(RED_THREADS)
+reduce_kernel(F f, const T* __restrict__ x, const T* __restrict__ y, size_t n_real,
+              double* __restrict__ partials, unsigned int* __restrict__ ticket,
+              double* __restrict__ out) {
+  constexpr int NOUT = CX ? F::NOUT_CX : F::NOUT_REAL;
+  constexpr int MODE = F::MODE;
+  constexpr int V = Vec16<T>::N;
+  double acc[NOUT];
+#pragma unroll
+  for (int k = 0; k < NOUT; ++k) acc[k] = ident<MODE>();
+
+  const size_t stride = (size_t)gridDim.x * RED_THREADS;
+  size_t i = (size_t)blockIdx.x * RED_THREADS + threadIdx.x;
+  if (VEC) {
+    const size_t nvec = n_real / V;
+    for (; i + (RED_UNROLL - 1) * stride < nvec; i += RED_UNROLL * stride) {
+      Vec16<T> vx[RED_UNROLL], vy[RED_UNROLL];
+#pragma unroll
+      for (int u = 0; u < RED_UNROLL; ++u) vx[u] = load_vec(x + (i + u * stride) * V);
+      if (F::HAS_Y) {
+#pragma unroll
+        for (int u = 0; u < RED_UNROLL; ++u) vy[u] = load_vec(y + (i + u * stride) * V);
+      }
+#pragma unroll
+      for (int u = 0; u < RED_UNROLL; ++u) consume_vec<T, CX>(f, acc, vx[u], F::HAS_Y ? vy[u] : vx[u]);
+    }
+    for (; i < nvec; i += stride) {
+      Vec16<T> vx = load_vec(x + i * V);
+      Vec16<T> vy = vx;
+      if (F::HAS_Y) vy = load_vec(y + i * V);
+      consume_vec<T, CX>(f, acc, vx, vy);
+    }
+    // tail scalars (only possible for real data; complex pairs never split a vector
+    // except T=float with an odd complex count -> one trailing pair)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      size_t t = nvec * V;
+      if (!CX) {
+        for (; t < n_real; ++t) f.real(acc, x[t], F::HAS_Y ? y[t] : x[t]);
+      } else {
+        for (; t + 1 < n_real; t += 2)
+          f.cx(acc, x[t], x[t + 1], F::HAS_Y ? y[t] : x[t], F::HAS_Y ? y[t + 1] : x[t + 1]);
+      }
+    }
+  } else {
+    if (!CX) {
+      for (; i < n_real; i += stride) f.real(acc, x[i], F::HAS_Y ? y[i] : x[i]);
+    } else {
+      const size_t nc = n_real / 2;
+      for (; i < nc; i += stride)
+        f.cx(acc, x[2 * i], x[2 * i + 1], F::HAS_Y ? y[2 * i] : x[2 * i],
+             F::HAS_Y ? y[2 * i + 1] : x[2 * i + 1]);
+    }
+  }
+
+  // block reduce
+  __shared__ double smem[NOUT][RED_THREADS / 32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NOUT; ++k) {
+    double v = warp_comb<MODE>(acc[k]);
+    if (lane == 0) smem[k][warp] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) {
+      double v = lane < RED_THREADS / 32 ? smem[k][lane] : ident<MODE>();
+      v = warp_comb<MODE>(v);
+      if (lane == 0) partials[(size_t)blockIdx.x * NOUT + k] = v;
+    }
+  }
+  // last-CTA fold in CTA order (deterministic)
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < NOUT; ++k) {
+        double v = ident<MODE>();
+        // lane l folds CTAs l, l+32, ... in increasing order
+        for (unsigned int b = lane; b < gridDim.x; b += 32)
+          v = comb<MODE>(v, __ldcg(&partials[(size_t)b * NOUT + k]));
+        v = warp_comb<MODE>(v);
+        if (lane == 0) out[k] = v;
+      }
+      if (lane == 0) *ticket = 0u;
+    }
+  }
+}
+
+inline int red_grid(const b2_ctx* ctx, size_t n_items) {
+  size_t need = (n_items + (size_t)RED_THREADS * RED_UNROLL - 1) / ((size_t)RED_THREADS * RED_UNROLL);
+  size_t cap = (size_t)ctx->sm_count * 8;
+  if (cap > (size_t)B2_RED_MAX_BLOCKS) cap = B2_RED_MAX_BLOCKS;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+template <typename T, bool CX, typename F>
+int launch_reduce(b2_ctx* ctx, F f, const void* x, const void* y, size_t n_real, double* out,
+                  cudaStream_t st) {
+  constexpr int V = Vec16<T>::N;
+  const bool vec = b2_aligned16(x) && (!F::HAS_Y || b2_aligned16(y)) && n_real >= (size_t)V;
+  int grid = red_grid(ctx, vec ? n_real / V : n_real);
+  if (vec)
+    reduce_kernel<T, CX, true, F><<<grid, RED_THREADS, 0, st>>>(f, (const T*)x, (const T*)y, n_real, ctx->red_partials, ctx->tickets, out);
+  else
+    reduce_kernel<T, CX, false, F><<<grid, RED_THREADS, 0, st>>>(f, (const T*)x, (const T*)y, n_real, ctx->red_partials, ctx->tickets, out);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+template <typename F>
+int dispatch_reduce(b2_ctx* ctx, F f, const void* x, const void* y, size_t n, int dtype,
+                    double* out, cudaStream_t st) {
+  switch (dtype) {
+    case B2_F32: return launch_reduce<float, false, F>(ctx, f, x, y, n, out, st);
+    case B2_F64: return launch_reduce<double, false, F>(ctx, f, x, y, n, out, st);
+    case B2_C64: return launch_reduce<float, true, F>(ctx, f, x, y, 2 * n, out, st);
+    case B2_C128: return launch_reduce<double, true, F>(ctx, f, x, y, 2 * n, out, st);
+    default: return B2_ERR_DTYPE;
+  }
+}
+
+__global__ void zero_out_kernel(double* out, int k, double v) {
+  if ((int)threadIdx.x < k) out[threadIdx.x] = v;
+}
+
+// ---- k real/complex dots in one launch ---------------------------------------
+struct MultiPtrs {
+  const void* x[4];
+  const void* y[4];
+};
+
+template <typename T, bool CX, bool CONJ, int K>
+__global__ void __launch_bounds__(RED_THREADS)
+dot_multi_kernel(MultiPtrs p, size_t n_real, double* __restrict__ partials,
+                 unsigned int* __restrict__ ticket, double* __restrict__ out) {
+  constexpr int PER = CX ? 2 : 1;
+  constexpr int NOUT = K * PER;
+  double acc[NOUT];
+#pragma unroll
+  for (int k = 0; k < NOUT; ++k) acc[k] = 0.0;
+  DotF<CONJ> f{0.0};
+  const size_t stride = (size_t)gridDim.x * RED_THREADS;
+  if (!CX) {
+    for (size_t i = (size_t)blockIdx.x * RED_THREADS + threadIdx.x; i < n_real; i += stride) {
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+        f.real(acc + k, ((const T*)p.x[k])[i], ((const T*)p.y[k])[i]);
+    }
+  } else {
+    const size_t nc = n_real / 2;
+    for (size_t i = (size_t)blockIdx.x * RED_THREADS + threadIdx.x; i < nc; i += stride) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const T* xx = (const T*)p.x[k];
+        const T* yy = (const T*)p.y[k];
+        f.cx(acc + 2 * k, xx[2 * i], xx[2 * i + 1], yy[2 * i], yy[2 * i + 1]);
+      }
+    }
+  }
+  __shared__ double smem[NOUT][RED_THREADS / 32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NOUT; ++k) {
+    double v = warp_sum(acc[k]);
+    if (lane == 0) smem[k][warp] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) {
+      double v = lane < RED_THREADS / 32 ? smem[k][lane] : 0.0;
+      v = warp_sum(v);
+      if (lane == 0) partials[(size_t)blockIdx.x * NOUT + k] = v;
+    }
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < NOUT; ++k) {
+        double v = 0.0;
+        for (unsigned int b = lane; b < gridDim.x; b += 32) v += __ldcg(&partials[(size_t)b * NOUT + k]);
+        v = warp_sum(v);
+        if (lane == 0) out[k] = v;
+      }
+      if (lane == 0) *ticket = 0u;
+    }
+  }
+}
+
+template <typename T, bool CX, bool CONJ>
+int launch_multi(b2_ctx* ctx, int k, const MultiPtrs& p, size_t n_real, double* out,
+                 cudaStream_t st) {
+  int grid = red_grid(ctx, n_real);
+  switch (k) {
+    case 1: dot_multi_kernel<T, CX, CONJ, 1><<<grid, RED_THREADS, 0, st>>>(p, n_real, ctx->red_partials, ctx->tickets, out); break;
+    case 2: dot_multi_kernel<T, CX, CONJ, 2><<<grid, RED_THREADS, 0, st>>>(p, n_real, ctx->red_partials, ctx->tickets, out); break;
+    case 3: dot_multi_kernel<T, CX, CONJ, 3><<<grid, RED_THREADS, 0, st>>>(p, n_real, ctx->red_partials, ctx->tickets, out); break;
+    case 4: dot_multi_kernel<T, CX, CONJ, 4><<<grid, RED_THREADS, 0, st>>>(p, n_real, ctx->red_partials, ctx->tickets, out); break;
+    default: return B2_ERR_ARG;
+  }
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+}  // namespace
+
+extern "C" int b2_dot(b2_ctx* ctx, const void* x, const void* y, size_t n, int dtype, int conj_x,
+                      double* out_dev, void* stream) {
+  if (!ctx || !out_dev) return B2_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    zero_out_kernel<<<1, 32, 0, st>>>(out_dev, 2, 0.0);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+  }
+  if (!x || !y) return B2_ERR_ARG;
+  const bool cx = (dtype == B2_C64 || dtype == B2_C128);
+  if (!cx) {  // imaginary part of a real dot is 0
+    zero_out_kernel<<<1, 32, 0, st>>>(out_dev, 2, 0.0);
+    B2_LAUNCH_CHECK();
+  }
+  if (conj_x) return dispatch_reduce(ctx, DotF<true>{0.0}, x, y, n, dtype, out_dev, st);
+  return dispatch_reduce(ctx, DotF<false>{0.0}, x, y, n, dtype, out_dev, st);
+}
+
+extern "C" int b2_norm_partial(b2_ctx* ctx, const void* x, size_t n, int dtype, int kind,
+                               double p, double* out_dev, void* stream) {
+  if (!ctx || !out_dev) return B2_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    zero_out_kernel<<<1, 32, 0, st>>>(out_dev, 1, kind == B2_NRM_MIN_ABS ? INFINITY : 0.0);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+  }
+  if (!x) return B2_ERR_ARG;
+  switch (kind) {
+    case B2_NRM_COUNT_NONZERO: return dispatch_reduce(ctx, CountNzF{0.0}, x, nullptr, n, dtype, out_dev, st);
+    case B2_NRM_SUM_ABS: return dispatch_reduce(ctx, SumAbsF{0.0}, x, nullptr, n, dtype, out_dev, st);
+    case B2_NRM_SUM_SQ: return dispatch_reduce(ctx, SumSqF{0.0}, x, nullptr, n, dtype, out_dev, st);
+    case B2_NRM_MAX_ABS: return dispatch_reduce(ctx, ExtAbsF<MODE_MAX>{0.0}, x, nullptr, n, dtype, out_dev, st);
+    case B2_NRM_MIN_ABS: return dispatch_reduce(ctx, ExtAbsF<MODE_MIN>{0.0}, x, nullptr, n, dtype, out_dev, st);
+    case B2_NRM_SUM_POW: return dispatch_reduce(ctx, SumPowF{p}, x, nullptr, n, dtype, out_dev, st);
+    default: return B2_ERR_ARG;
+  }
+}
+
+extern "C" int b2_dot_multi(b2_ctx* ctx, int k, const void* const* xs, const void* const* ys,
+                            size_t n, int dtype, int conj_x, double* out_dev, void* stream) {
+  if (!ctx || !out_dev || !xs || !ys || k < 1 || k > 4) return B2_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    zero_out_kernel<<<1, 32, 0, st>>>(out_dev, 2 * k, 0.0);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+  }
+  MultiPtrs p;
+  for (int i = 0; i < k; ++i) {
+    p.x[i] = xs[i];
+    p.y[i] = ys[i];
+  }
+  // output layout: k (re, im) pairs; real dtypes write re only -> zero first
+  const bool cx = (dtype == B2_C64 || dtype == B2_C128);
+  if (!cx) {
+    // real: kernel writes out[0..k); repack to (re,im) pairs is done by the caller reading
+    // out[j] for j<k.  Keep the layout simple: real dtypes -> k doubles.
+    switch (dtype) {
+      case B2_F32: return launch_multi<float, false, false>(ctx, k, p, n, out_dev, st);
+      case B2_F64: return launch_multi<double, false, false>(ctx, k, p, n, out_dev, st);
+    }
+    return B2_ERR_DTYPE;
+  }
+  if (dtype == B2_C64)
+    return conj_x ? launch_multi<float, true, true>(ctx, k, p, 2 * n, out_dev, st)
+                  : launch_multi<float, true, false>(ctx, k, p, 2 * n, out_dev, st);
+  return conj_x ? launch_multi<double, true, true>(ctx, k, p, 2 * n, out_dev, st)
+                : launch_multi<double, true, false>(ctx, k, p, 2 * n, out_dev, st);
+}

@@ -1,0 +1,84 @@
+"""Rank-local dense operators: the role third-party ``pylops`` operators play
+inside MPIBlockDiag / MPIVStack in the reference (BlockDiag.py:127-129,
+VStack.py:129-131 call ``oper.matvec`` on a slice of the local array).
+
+Any object with ``shape``, ``dtype``, ``matvec(x)``, ``rmatvec(x)`` acting on
+1-D device tensors can be used; :class:`MatrixMult` is the dense block every
+reference test / BASELINE config uses, applied by the b2_gemv kernels.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = ["MatrixMult", "LocalOperator"]
+
+
+class LocalOperator:
+    """minimal rank-local linear operator interface"""
+    shape = (0, 0)
+    dtype = np.float64
+
+    def matvec(self, x: torch.Tensor) -> torch.Tensor:
+        return self._matvec(x)
+
+    def rmatvec(self, x: torch.Tensor) -> torch.Tensor:
+        return self._rmatvec(x)
+
+    # pylops-style aliases (MPILinearOperator(Op=...) calls Op._matvec)
+    def _matvec(self, x):
+        raise NotImplementedError
+
+    def _rmatvec(self, x):
+        raise NotImplementedError
+
+
+class MatrixMult(LocalOperator):
+    """Dense block ``y = A x`` / ``y = A^H x`` (pylops.MatrixMult for a single
+    right-hand side).  ``A`` may be a NumPy array (uploaded once) or a device
+    tensor; dtype float32/float64/complex64/complex128, or bfloat16 with
+    float32 vectors.  HBM-bound GEMV kernels (csrc/gemv.cu)."""
+
+    def __init__(self, A, dtype=None):
+        if not isinstance(A, torch.Tensor):
+            A = torch.as_tensor(np.asarray(A))
+        if dtype is not None:
+            A = A.to(_lib.torch_dtype(dtype))
+        if A.dim() != 2:
+            raise ValueError("MatrixMult expects a 2-D array")
+        _lib.ctx()
+        self.A = A.to("cuda").contiguous()
+        self.shape = (int(A.shape[0]), int(A.shape[1]))
+        self._tdtype = self.A.dtype
+        self._xdtype = torch.float32 if self._tdtype is torch.bfloat16 else self._tdtype
+        self.dtype = _lib.numpy_dtype(self._xdtype)
+
+    def _apply(self, x: torch.Tensor, op: int, out=None) -> torch.Tensor:
+        m, n = self.shape
+        x = x.reshape(-1)
+        if x.dtype != self._xdtype:
+            x = x.to(self._xdtype)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        nin, nout = (n, m) if op == _lib.OP_N else (m, n)
+        if x.numel() != nin:
+            raise ValueError(f"dimension mismatch: operator {self.shape}, vector {x.numel()}")
+        y = torch.empty(nout, dtype=self._xdtype, device=x.device) if out is None else out
+        _lib.check(_lib.lib.b2_gemv(_lib.ctx(), self.A.data_ptr(), n, m, n, x.data_ptr(), y.data_ptr(),
+                                    op, _lib.code(self._tdtype), _lib.code(self._xdtype), _lib.stream()),
+                   "b2_gemv")
+        return y
+
+    def _matvec(self, x, out=None):
+        return self._apply(x, _lib.OP_N, out)
+
+    def _rmatvec(self, x, out=None):
+        return self._apply(x, _lib.OP_H, out)
+
+    def matvec(self, x, out=None):
+        return self._apply(x, _lib.OP_N, out)
+
+    def rmatvec(self, x, out=None):
+        return self._apply(x, _lib.OP_H, out)

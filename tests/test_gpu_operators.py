@@ -1,0 +1,311 @@
+"""GPU parity tests, operator level (world_size 1): the reference-facing API
+(DistributedArray, MPI* operators, dottest, cgls) against the CPU oracle and
+the reference's own known-answer vectors.  Multi-rank runs of the same checks
+live in tests/test_gpu_multi.py (needs >= 2 GPUs)."""
+import numpy as np
+import pytest
+import torch
+
+import pylops_mpi_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pm():
+    import pylops_mpi_b200 as pm
+    return pm
+
+
+def host(t):
+    return t.cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+
+
+# ---- DistributedArray: test_distributedarray.py ------------------------------------------
+@pytest.mark.parametrize("shape,axis", [((500, 501), 1), ((501, 500), 0), ((200, 31, 11), 1), ((600,), 0)])
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32])
+def test_creation_to_dist_math(pm, shape, axis, dtype):
+    np.random.seed(42)
+    a = np.random.normal(100, 100, shape).astype(dtype)
+    b = np.random.normal(300, 300, shape).astype(dtype)
+    if np.issubdtype(dtype, np.complexfloating):
+        a = a + 1j * np.random.normal(0, 50, shape)
+        b = b - 1j * np.random.normal(0, 50, shape)
+    A = pm.DistributedArray.to_dist(a, axis=axis)
+    B = pm.DistributedArray.to_dist(b, axis=axis)
+    assert A.global_shape == shape and A.local_shape == shape and A.local_shapes == [shape]
+    assert A.partition is pm.Partition.SCATTER and A.axis == axis and A.dtype == np.dtype(dtype)
+    tol = dict(rtol=1e-5) if dtype == np.float32 else dict(rtol=1e-14)
+    np.testing.assert_allclose(host((A + B).asarray()), a + b, **tol)
+    np.testing.assert_allclose(host((A - B).asarray()), a - b, **tol)
+    np.testing.assert_allclose(host((A * B).asarray()), a * b, **tol)
+    np.testing.assert_allclose(host((A * 3.5).asarray()), a * 3.5, **tol)
+    np.testing.assert_allclose(host((2 * A).asarray()), 2 * a, **tol)
+    np.testing.assert_allclose(host((-A).asarray()), -a, **tol)
+    np.testing.assert_allclose(host(A.conj().asarray()), a.conj(), **tol)
+    Cc = A.copy()
+    Cc += B
+    Cc -= A
+    np.testing.assert_allclose(host(Cc.asarray()), b, rtol=1e-4 if dtype == np.float32 else 1e-12)
+    assert np.all(host(A.zeros_like().asarray()) == 0)
+    r = A.ravel()
+    assert r.global_shape == (int(np.prod(shape)),)
+    np.testing.assert_array_equal(host(r.asarray()), a.ravel())
+    # dot / norm (test_distributedarray.py:201-222)
+    scale = np.linalg.norm(a) * np.linalg.norm(b)
+    rt = 1e-5 if dtype == np.float32 else 1e-13
+    assert abs(A.dot(B)[0] - np.dot(a.ravel().astype(np.complex128), b.ravel().astype(np.complex128))) <= rt * scale
+    assert abs(A.dot(B, vdot=True)[0] - np.vdot(a.ravel().astype(np.complex128), b.ravel().astype(np.complex128))) <= rt * scale
+    for ord_ in (None, 1, 2, np.inf, -np.inf, 0, 3):
+        ref = np.linalg.norm(a.ravel().astype(np.complex128), 2 if ord_ is None else ord_)
+        got = A.norm(ord_)
+        assert got.dtype == np.float64 and got.shape == (1,)
+        np.testing.assert_allclose(got[0], ref, rtol=rt)
+
+
+def test_broadcast_and_errors(pm):
+    x = np.arange(12.0).reshape(3, 4)
+    B = pm.DistributedArray.to_dist(x, partition=pm.Partition.BROADCAST)
+    assert B.local_shape == (3, 4)
+    np.testing.assert_allclose(B.dot(B)[0], (x * x).sum())
+    np.testing.assert_allclose(B.norm()[0], np.linalg.norm(x))
+    with pytest.raises(IndexError):
+        pm.DistributedArray(global_shape=(3,), axis=1)
+    with pytest.raises(ValueError):
+        pm.DistributedArray(global_shape=(3,), local_shapes=[(2,)])
+    S = pm.DistributedArray.to_dist(x)
+    with pytest.raises(ValueError):
+        S + B
+    with pytest.raises(ValueError):
+        S.add(pm.DistributedArray.to_dist(np.zeros((3, 5))))
+    g = S.add_ghost_cells(cells_front=1, cells_back=1)
+    np.testing.assert_array_equal(host(g), x)
+    assert S.redistribute(1).axis == 1
+
+
+# ---- MPIFirstDerivative: config 1 and the test_derivative.py grid ----------------------------
+def test_config1_readme_flow(pm):
+    """README.md:73-94 / plot_derivative.py:36-43 + dottest + cgls(niter=10)"""
+    nz, nx = 11, 21
+    x = np.zeros((nz, nx))
+    x[nz // 2, nx // 2] = 1.0
+    xd = pm.DistributedArray.to_dist(x.ravel())
+    Fop = pm.MPIFirstDerivative((nz, nx), dtype=np.float64)
+    y = Fop @ xd
+    yh = host(y.asarray()).reshape(nz, nx)
+    expect = np.zeros((nz, nx))
+    expect[4, 10], expect[6, 10] = 0.5, -0.5
+    assert np.array_equal(yh, expect)
+    # the oracle at P=2 (the reference's run) gives the same global answer
+    ref = np.concatenate(o.first_derivative(o.to_dist(x.ravel(), 2), (nz, nx)))
+    assert np.array_equal(yh.ravel(), ref)
+    u = pm.DistributedArray.to_dist(np.random.default_rng(42).normal(0, 10, nz * nx))
+    v = pm.DistributedArray.to_dist(np.random.default_rng(43).normal(0, 10, nz * nx))
+    assert pm.dottest(Fop, u, v, rtol=1e-6)
+    # cgls 10 iterations vs the oracle (P=2 simulation of the reference)
+    x0 = pm.DistributedArray.to_dist(np.zeros(nz * nx))
+    xinv, istop, iit, r1, r2, cost = pm.cgls(Fop, y, x0=x0, niter=10, tol=0.0)
+    mv = lambda a: o.SimArray(o.first_derivative(a.locs, (nz, nx)))                  # noqa: E731
+    rmv = lambda a: o.SimArray(o.first_derivative(a.locs, (nz, nx), adjoint=True))   # noqa: E731
+    yo = mv(o.SimArray(o.to_dist(x.ravel(), 2)))
+    # the oracle's y lives on the row-block partition; cgls data must be flat-balanced like ours
+    xo, istop_o, iit_o, r1o, r2o, cost_o = o.cgls(mv, rmv, o.SimArray(o.to_dist(yo.asarray(), 2)),
+                                                  o.SimArray(o.to_dist(np.zeros(nz * nx), 2)), niter=10, tol=0.0)
+    assert iit == iit_o == 10 and istop == istop_o
+    np.testing.assert_allclose(host(xinv.asarray()), xo.asarray(), rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(cost, cost_o, rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose([r1, r2], [r1o, r2o], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("dims,h", [(600, 1.0), ((100, 151), 1.0), ((101, 51, 10), 0.4), ((79, 11, 5), 0.4)])
+@pytest.mark.parametrize("kind,order", [("forward", 3), ("backward", 3), ("centered", 3), ("centered", 5)])
+@pytest.mark.parametrize("edge", [False, True])
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+@pytest.mark.parametrize("part", ["SCATTER", "BROADCAST"])
+def test_first_derivative_operator_grid(pm, dims, h, kind, order, edge, dtype, part):
+    # tests/test_derivative.py:33-160, 198-295
+    dimsT = (dims,) if np.isscalar(dims) else dims
+    n = int(np.prod(dimsT))
+    rng = np.random.default_rng(42)
+    x = rng.normal(0, 10, n).astype(dtype)
+    if np.issubdtype(dtype, np.complexfloating):
+        x = x + 1j * rng.normal(0, 10, n)
+    Fop = pm.MPIFirstDerivative(dims, sampling=h, kind=kind, edge=edge, order=order, dtype=dtype)
+    xd = pm.DistributedArray.to_dist(x, partition=getattr(pm.Partition, part))
+    D = o.first_derivative_dense(dimsT[0], h, kind, edge, order)
+    X = x.reshape(dimsT[0], -1)
+    y = Fop @ xd
+    ya = Fop.H @ xd
+    assert y.partition is pm.Partition.SCATTER
+    np.testing.assert_allclose(host(y.asarray()), (D @ X).ravel(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(host(ya.asarray()), (D.T @ X).ravel(), rtol=1e-12, atol=1e-12)
+    u = pm.DistributedArray.to_dist(rng.normal(0, 10, n).astype(dtype))
+    v = pm.DistributedArray.to_dist(rng.normal(0, 10, n).astype(dtype))
+    assert pm.dottest(Fop, u, v)
+
+
+def test_first_derivative_errors(pm):
+    with pytest.raises(NotImplementedError):
+        pm.MPIFirstDerivative(10, kind="sideways")
+    with pytest.raises(NotImplementedError):
+        pm.MPIFirstDerivative(10, kind="centered", order=7)
+    Fop = pm.MPIFirstDerivative(10)
+    with pytest.raises(ValueError, match="dimension mismatch"):
+        Fop.matvec(pm.DistributedArray.to_dist(np.zeros(11)))
+    with pytest.raises(ValueError):
+        Fop.matvec(pm.DistributedArray.to_dist(np.zeros(10), partition=pm.Partition.UNSAFE_BROADCAST))
+
+
+# ---- BlockDiag / VStack / HStack KATs (test_blockdiag.py:24-71, test_stack.py:29-79) ------------
+@pytest.mark.parametrize("ny,nx", [(101, 101), (301, 101)])
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32])
+def test_blockdiag_vstack_kats(pm, ny, nx, dtype):
+    rank = 0
+    A = ((rank + 1) * np.ones((ny, nx))).astype(dtype)
+    Op = pm.MatrixMult(A, dtype=dtype)
+    BD = pm.MPIBlockDiag([Op])
+    assert BD.shape == (ny, nx)
+    x = pm.DistributedArray.to_dist(np.ones(nx, dtype=dtype))
+    y = BD @ x
+    np.testing.assert_allclose(host(y.asarray()), nx * np.ones(ny), rtol=1e-6)
+    xa = BD.H @ pm.DistributedArray.to_dist(np.ones(ny, dtype=dtype))
+    np.testing.assert_allclose(host(xa.asarray()), ny * np.ones(nx), rtol=1e-6)
+    assert pm.dottest(BD, x, pm.DistributedArray.to_dist(np.ones(ny, dtype=dtype)))
+    # two blocks on one rank, random data, vs oracle
+    rng = np.random.default_rng(1)
+    A2 = rng.standard_normal((ny // 2, nx)).astype(dtype)
+    BD2 = pm.MPIBlockDiag([Op, pm.MatrixMult(A2)])
+    xv = rng.standard_normal(2 * nx).astype(dtype)
+    ref = o.blockdiag([[A, A2]], [xv])[0]
+    np.testing.assert_allclose(host((BD2 @ pm.DistributedArray.to_dist(xv)).asarray()), ref, rtol=1e-4 if dtype == np.float32 else 1e-12)
+    VS = pm.MPIVStack([Op, pm.MatrixMult(A2)])
+    xb = pm.DistributedArray.to_dist(rng.standard_normal(nx).astype(dtype), partition=pm.Partition.BROADCAST)
+    yv = VS @ xb
+    assert yv.partition is pm.Partition.SCATTER
+    tol = 1e-4 if dtype == np.float32 else 1e-12
+    np.testing.assert_allclose(host(yv.asarray()), o.vstack_matvec([[A, A2]], host(xb.local_array))[0], rtol=tol, atol=tol)
+    xr = VS.H @ yv
+    assert xr.partition is pm.Partition.BROADCAST
+    np.testing.assert_allclose(host(xr.asarray()), o.vstack_rmatvec([[A, A2]], [host(yv.asarray())]), rtol=tol * 10, atol=tol * 100)
+    with pytest.raises(ValueError):
+        VS @ pm.DistributedArray.to_dist(np.ones(nx, dtype=dtype))
+    HS = pm.MPIHStack([pm.MatrixMult(A.T.copy())])
+    np.testing.assert_allclose(host((HS @ pm.DistributedArray.to_dist(np.ones(ny, dtype=dtype))).asarray()),
+                               ny * np.ones(nx), rtol=1e-6)
+
+
+# ---- MPIMatrixMult KATs (test_matrixmult.py:37-60, 82-166, 199-271) ----------------------------
+@pytest.mark.parametrize("N,K,M,dtype", [(64, 64, 64, np.float64), (37, 37, 37, np.float64), (50, 30, 40, np.float64),
+                                         (22, 20, 16, np.complex128), (3, 4, 5, np.float32), (1, 2, 1, np.float64),
+                                         (2, 1, 3, np.float32), (64, 48, 1, np.float64)])
+@pytest.mark.parametrize("kind", ["summa", "block"])
+def test_matrixmult_kats(pm, N, K, M, dtype, kind):
+    A = np.arange(N * K, dtype=dtype).reshape(N, K)
+    X = np.arange(K * M, dtype=dtype).reshape(K, M)
+    if np.issubdtype(dtype, np.complexfloating):
+        A = A + 0.5j * A
+        X = X + 0.7j * X
+    Aop = pm.MPIMatrixMult(A, M, kind=kind, dtype=dtype)
+    x = pm.DistributedArray.to_dist(X.ravel())
+    y = Aop @ x
+    rtol = np.finfo(dtype).resolution * 10
+    Yref = (A.astype(np.complex128) @ X.astype(np.complex128)) if np.iscomplexobj(A) else A.astype(np.float64) @ X
+    np.testing.assert_allclose(host(y.asarray()).reshape(N, M), Yref, rtol=rtol)
+    xadj = Aop.H @ y
+    np.testing.assert_allclose(host(xadj.asarray()).reshape(K, M), A.conj().T @ Yref, rtol=rtol * 10)
+    with pytest.raises(ValueError):
+        Aop @ pm.DistributedArray.to_dist(X.ravel(), partition=pm.Partition.BROADCAST)
+
+
+# ---- MPIFredholm1 KATs (test_fredholm.py:36-95, 114-167) ---------------------------------------
+@pytest.mark.parametrize("nz", [5, 1])
+@pytest.mark.parametrize("dtype", [np.float32, np.complex64, np.float64])
+@pytest.mark.parametrize("saveGt,usematmul", [(True, True), (False, False)])
+def test_fredholm1_kat(pm, nz, dtype, saveGt, usematmul):
+    cx = np.issubdtype(dtype, np.complexfloating)
+    nsl, nx, ny = 21, 4, 6
+    G = np.arange(nsl * nx * ny, dtype=np.float64).reshape(nsl, nx, ny)
+    G = (G - 1j * G) if cx else G
+    x = (np.ones((nsl, ny, nz)) + (1j if cx else 0)).astype(dtype)
+    Fop = pm.MPIFredholm1(G.astype(dtype), nz=nz, saveGt=saveGt, usematmul=usematmul, dtype=dtype)
+    xd = pm.DistributedArray.to_dist(x.ravel(), partition=pm.Partition.BROADCAST)
+    y = Fop @ xd
+    assert y.partition is pm.Partition.BROADCAST
+    ref = o.fredholm1([G], x.ravel().astype(G.dtype), nz)
+    np.testing.assert_allclose(host(y.asarray()), ref, rtol=1e-5)
+    xa = Fop.H @ y
+    refa = o.fredholm1([G], ref, nz, adjoint=True)
+    np.testing.assert_allclose(host(xa.asarray()), refa, rtol=1e-4)
+    with pytest.raises(ValueError):
+        Fop @ pm.DistributedArray.to_dist(x.ravel())
+    yv = pm.DistributedArray.to_dist(np.ones(nsl * nx * nz, dtype=dtype), partition=pm.Partition.BROADCAST)
+    assert pm.dottest(Fop, xd, yv, rtol=1e-4)
+
+
+# ---- operator algebra (test_linearop.py) ---------------------------------------------------------
+def test_operator_algebra(pm):
+    rng = np.random.default_rng(0)
+    n = 64
+    A = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    Op = pm.MPIBlockDiag([pm.MatrixMult(A)])
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    xd = pm.DistributedArray.to_dist(x)
+    chk = lambda got, ref: np.testing.assert_allclose(host(got.asarray()), ref, rtol=1e-11)  # noqa: E731
+    chk(Op.H @ xd, A.conj().T @ x)
+    chk(Op.T @ xd, A.T @ x)
+    chk(Op.conj() @ xd, A.conj() @ x)
+    chk((Op * Op) @ xd, A @ (A @ x))
+    chk((Op + Op) @ xd, 2 * A @ x)
+    chk((Op - Op.H) @ xd, (A - A.conj().T) @ x)
+    chk((3j * Op) @ xd, 3j * (A @ x))
+    chk((3j * Op).H @ xd, np.conj(3j) * (A.conj().T @ x))
+    chk((-Op) @ xd, -(A @ x))
+    chk((Op ** 3) @ xd, A @ (A @ (A @ x)))
+    chk(pm.asmpilinearoperator(Op) * xd, A @ x)
+    with pytest.raises(ValueError):
+        Op @ 3.0
+
+
+# ---- CGLS on BlockDiag (test_solver.py:44-100, 150-196) -----------------------------------------
+@pytest.mark.parametrize("ny,nx", [(11, 11), (31, 11)])
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128])
+def test_cgls_blockdiag_vs_oracle(pm, ny, nx, dtype):
+    rng = np.random.default_rng(42)
+    A = np.ones((ny, nx), dtype=dtype)
+    blk = A.conj().T @ A + 1e-5 * np.eye(nx, dtype=dtype)
+    Op = pm.MPIBlockDiag([pm.MatrixMult(blk)])
+    xt = rng.normal(1, 10, nx).astype(dtype)
+    if np.issubdtype(dtype, np.complexfloating):
+        xt = xt + 1j * rng.normal(10, 10, nx)
+    y = Op @ pm.DistributedArray.to_dist(xt)
+    for x0v in (np.zeros(nx, dtype=dtype), rng.normal(0, 10, nx).astype(dtype)):
+        xinv, istop, iit, r1, r2, cost = pm.cgls(Op, y, x0=pm.DistributedArray.to_dist(x0v), niter=nx, tol=1e-5)
+        mv = lambda a: o.SimArray(o.blockdiag([[blk]], a.locs))                  # noqa: E731
+        rmv = lambda a: o.SimArray(o.blockdiag([[blk]], a.locs, adjoint=True))   # noqa: E731
+        xo, istop_o, iit_o, r1o, r2o, cost_o = o.cgls(mv, rmv, mv(o.SimArray([xt])), o.SimArray([x0v]), niter=nx, tol=1e-5)
+        assert (istop, iit) == (istop_o, iit_o)
+        np.testing.assert_allclose(host(xinv.asarray()), xo.asarray(), rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(cost, cost_o, rtol=1e-5, atol=1e-8)
+    xcg, itcg, costcg = pm.cg(Op, y, x0=pm.DistributedArray.to_dist(np.zeros(nx, dtype=dtype)), niter=nx, tol=1e-5)
+    xo, ito, costo = o.cg(mv, mv(o.SimArray([xt])), o.SimArray([np.zeros(nx, dtype=dtype)]), niter=nx, tol=1e-5)
+    assert itcg == ito
+    np.testing.assert_allclose(host(xcg.asarray()), xo.asarray(), rtol=1e-6, atol=1e-8)
+
+
+def test_cgls_config3_single_block_fp32(pm):
+    """BASELINE config 3 restricted to one 4096x4096 float32 block: 50 iterations reach the
+    float64 oracle solution to 1e-6 relative"""
+    n = 4096
+    A = (np.random.default_rng(100).standard_normal((n, n), dtype=np.float32) / 128 + 2 * np.eye(n, dtype=np.float32))
+    xt = np.random.default_rng(7).standard_normal(n).astype(np.float32)
+    Op = pm.MPIBlockDiag([pm.MatrixMult(A)])
+    y = Op @ pm.DistributedArray.to_dist(xt)
+    xinv, istop, iit, r1, r2, cost = pm.cgls(Op, y, x0=pm.DistributedArray.to_dist(np.zeros(n, np.float32)), niter=50, tol=0.0)
+    assert iit == 50
+    A64 = A.astype(np.float64)
+    mv = lambda a: o.SimArray([A64 @ a.locs[0]])       # noqa: E731
+    rmv = lambda a: o.SimArray([A64.T @ a.locs[0]])    # noqa: E731
+    xo, *_rest, cost_o = o.cgls(mv, rmv, o.SimArray([A64 @ xt.astype(np.float64)]), o.SimArray([np.zeros(n)]), niter=50, tol=0.0)
+    rel = np.linalg.norm(host(xinv.asarray()) - xo.asarray()) / np.linalg.norm(xo.asarray())
+    assert rel < 1e-5, rel
+    assert np.linalg.norm(host(xinv.asarray()) - xt) / np.linalg.norm(xt) < 1e-5

@@ -1,0 +1,152 @@
+"""CPU tests of the host side: partition bookkeeping (bit-exact vs the oracle),
+exchange plans, the C-ABI library's symbol table, and the communicator shim on
+a world_size-2 gloo group.  No compute kernels are called."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import pylops_mpi_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_library_loads_and_exports_every_declared_symbol():
+    from pylops_mpi_b200 import build
+    path = build.build()            # builds on first use (nvcc cross-compiles without a GPU)
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "b200lops.h")).read()
+    declared = set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/b200lops.h but not exported"
+    assert lib.b2_version() == 100
+    lib.b2_strerror.restype = ctypes.c_char_p
+    assert b"halo" in lib.b2_strerror(2003)
+
+
+def test_python_binding_covers_header():
+    import pylops_mpi_b200._lib as L
+    header = open(os.path.join(ROOT, "include", "b200lops.h")).read()
+    declared = set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(L.EXPORTS)
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+    import pylops_mpi_b200 as pm
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pm._lib.B200Error):
+        pm.DistributedArray(global_shape=10)
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 231, 600, 1000003])
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 8, 9])
+def test_local_split_sizes_bit_exact(n, P):
+    from pylops_mpi_b200.utils.partition import local_split_sizes
+    assert local_split_sizes(n, P) == [o.local_split((n,), P, r)[0] for r in range(P)]
+
+
+@pytest.mark.parametrize("dims", [(11, 21), (600,), (100, 151), (101, 51, 100), (79, 101, 50)])
+@pytest.mark.parametrize("P", [1, 2, 3, 4, 8])
+def test_repartition_plan_moves_every_element_once(dims, P):
+    from pylops_mpi_b200.utils.partition import local_split_sizes, repartition_plan, reshaped_ghost_cells
+    n = int(np.prod(dims))
+    src = local_split_sizes(n, P)
+    dst = [e * int(np.prod(dims[1:])) for e in local_split_sizes(dims[0], P)]
+    x = np.arange(n)
+    xs = np.split(x, np.cumsum(src)[:-1])
+    out = [np.full(d, -1) for d in dst]
+    for r in range(P):
+        sends, _ = repartition_plan(src, dst, r)
+        for peer, off, cnt in sends:
+            _, recvs = repartition_plan(src, dst, peer)
+            doff = [q for q in recvs if q[0] == r][0]
+            assert doff[2] == cnt
+            out[peer][doff[1]:doff[1] + cnt] = xs[r][off:off + cnt]
+    assert np.array_equal(np.concatenate(out), x)
+    # and it agrees with the reference's neighbour-only plan whenever that plan is legal
+    try:
+        ref = o.reshaped_in([a.copy() for a in xs], [(e,) + tuple(dims[1:]) for e in local_split_sizes(dims[0], P)])
+    except ValueError:
+        return
+    for r in range(P):
+        assert np.array_equal(ref[r].ravel(), out[r])
+        cf, cb, idx = reshaped_ghost_cells(dst, src, r)
+        assert cf >= 0 and cb >= 0 and idx >= 0
+
+
+def test_halo_plan_matches_oracle_ghost_cells():
+    from pylops_mpi_b200.utils.partition import halo_plan, local_split_sizes
+    rows = local_split_sizes(101, 4)
+    for r in range(4):
+        p = halo_plan(rows, r, 2, 2)
+        assert p["recv_lo"] == (0 if r == 0 else 2) and p["recv_hi"] == (0 if r == 3 else 2)
+        assert p["send_lo"] == (0 if r == 0 else 2) and p["send_hi"] == (0 if r == 3 else 2)
+    with pytest.raises(ValueError):
+        halo_plan([3, 1, 3], 0, 2, 2)
+
+
+def test_single_process_comm_shim():
+    from pylops_mpi_b200.comm import Comm
+    c = Comm(0, 1)
+    assert c.Get_rank() == 0 and c.Get_size() == 1
+    assert c.allgather((3, 4)) == [(3, 4)]
+    assert c.allreduce(5) == 5 and c.bcast("a") == "a"
+    s = c.Split(0, 0)
+    assert s.Get_size() == 1 and c.nccl is None
+    c.Barrier()
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "oracle"))
+import numpy as np
+import pylops_mpi_oracle as o
+from pylops_mpi_b200.comm import get_comm_world
+from pylops_mpi_b200.utils.partition import local_split_sizes, halo_plan
+from pylops_mpi_b200.DistributedArray import local_split, Partition
+comm = get_comm_world()
+rank, size = comm.Get_rank(), comm.Get_size()
+assert size == 2
+assert comm.allgather(rank * 10) == [0, 10]
+assert comm.allreduce(rank + 1) == 3
+assert comm.allreduce(rank + 1, "max") == 2
+assert comm.bcast({"a": rank}, root=1) == {"a": 1}
+# local_split through the communicator == oracle == closed formula
+for shape, axis in [((11, 21), 0), ((500, 501), 1), ((7,), 0)]:
+    mine = local_split(shape, comm, Partition.SCATTER, axis)
+    assert mine == o.local_split(shape, size, rank, o.SCATTER, axis)
+    assert comm.allgather(mine[axis]) == local_split_sizes(shape[axis], size)
+# Split: each rank alone, then everybody together with reversed keys
+solo = comm.Split(color=rank, key=0)
+assert solo.Get_size() == 1 and solo.Get_rank() == 0
+rev = comm.Split(color=0, key=size - rank)
+assert rev.Get_size() == 2 and rev.Get_rank() == 1 - rank
+assert rev.allgather(rank) == [1, 0]
+m = comm.split_by_mask([0, 0]); assert m.Get_size() == 2
+assert comm.split_by_mask([0, 0]) is m            # cached
+# halo plan is symmetric between neighbours
+rows = local_split_sizes(11, size)
+p = halo_plan(rows, rank, 1, 1)
+q = comm.allgather(p)
+assert q[0]["send_hi"] == q[1]["recv_lo"] and q[1]["send_lo"] == q[0]["recv_hi"]
+comm.Barrier()
+print("WORKER_OK", rank)
+'''
+
+
+def test_comm_shim_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29631", str(script), ROOT],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("WORKER_OK") == 2
