@@ -1,0 +1,220 @@
+"""Multi-rank parity worker: run under torchrun with one process per GPU.  Every
+check compares the B200 path at world size P with the CPU oracle simulating the
+reference at the same P (per-rank outputs, not just gathered ones)."""
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import pylops_mpi_oracle as o  # noqa: E402
+import pylops_mpi_b200 as pm  # noqa: E402
+
+comm = pm.get_comm_world()
+rank, P = comm.Get_rank(), comm.Get_size()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+def check(name, got, ref, rtol=1e-12, atol=1e-12):
+    np.testing.assert_allclose(got, ref, rtol=rtol, atol=atol, err_msg=f"[rank {rank}] {name}")
+
+
+# ---- DistributedArray ---------------------------------------------------------------------
+np.random.seed(42)
+for shape, axis in [((50, 51), 1), ((51, 50), 0), ((20, 21, 11), 1), ((600,), 0)]:
+    a = np.random.normal(100, 100, shape)
+    b = np.random.normal(300, 300, shape)
+    A = pm.DistributedArray.to_dist(a, axis=axis)
+    B = pm.DistributedArray.to_dist(b, axis=axis)
+    assert A.local_shape == o.local_split(shape, P, rank, o.SCATTER, axis)
+    assert A.local_shapes == o.local_shapes(shape, P, o.SCATTER, axis)
+    check("asarray", host(A.asarray()), a, 0, 0)
+    check("add", host((A + B).asarray()), a + b)
+    al, bl = o.to_dist(a, P, axis=axis), o.to_dist(b, P, axis=axis)
+    check("local", host(A.local_array), al[rank], 0, 0)
+    check("dot", A.dot(B)[0], o.dot(al, bl)[rank], 1e-13, 0)
+    for ord_ in (None, 1, np.inf, -np.inf, 0, 3):
+        check(f"norm{ord_}", A.norm(ord_)[0], o.norm(al, ord_)[rank], 1e-13, 0)
+    Bc = pm.DistributedArray.to_dist(a, partition=pm.Partition.BROADCAST)
+    check("bcast dot", Bc.dot(Bc)[0], np.dot(a.ravel(), a.ravel()), 1e-13, 0)
+    if len(shape) == 2:
+        R = A.redistribute(1 - axis)
+        check("redistribute", host(R.asarray()), a, 0, 0)
+        assert R.local_shape == o.local_split(shape, P, rank, o.SCATTER, 1 - axis)
+# masked sub-communicators (test_distributedarray.py:270-361)
+if P >= 2:
+    mask = [r % 2 for r in range(P)]
+    x = np.arange(24.0 * P)
+    X = pm.DistributedArray.to_dist(x, mask=mask)
+    xl = o.to_dist(x, P)
+    check("masked dot", X.dot(X)[0], o.dot(xl, xl, mask=mask)[rank], 1e-14, 0)
+    check("masked norm", X.norm(1)[0], o.norm(xl, 1, mask=mask)[rank], 1e-14, 0)
+# ghost cells
+G = pm.DistributedArray.to_dist(np.arange(40.0 * P).reshape(10 * P, 4))
+g = host(G.add_ghost_cells(cells_front=2, cells_back=1))
+ref = o.add_ghost_cells(o.to_dist(np.arange(40.0 * P).reshape(10 * P, 4), P), 0, [2] * P, [1] * P)[rank]
+check("ghost", g, ref, 0, 0)
+
+# ---- MPIFirstDerivative (config 1 at P = world size, plus the test_derivative grid) ---------------
+x = np.zeros((11, 21))
+x[5, 10] = 1.0
+Fop = pm.MPIFirstDerivative((11, 21))
+try:
+    refl = o.first_derivative(o.to_dist(x.ravel(), P), (11, 21))
+    y = Fop @ pm.DistributedArray.to_dist(x.ravel())
+    assert np.array_equal(host(y.local_array), refl[rank]), "config-1 KAT per-rank"
+except ValueError:
+    # the reference cannot run this split (P=8); the native re-partition can
+    y = Fop @ pm.DistributedArray.to_dist(x.ravel())
+    e = np.zeros((11, 21))
+    e[4, 10], e[6, 10] = 0.5, -0.5
+    assert np.array_equal(host(y.asarray()), e.ravel())
+rng = np.random.default_rng(42)
+for dims, h in [((600,), 1.0), ((100, 151), 1.0), ((101, 51, 10), 0.4), ((79, 11, 5), 0.4), ((64 * P, 256), 1.0)]:
+    for kind, order in [("forward", 3), ("backward", 3), ("centered", 3), ("centered", 5)]:
+        for edge in (False, True):
+            for dtype in (np.float64, np.complex128):
+                n = int(np.prod(dims))
+                xg = rng.normal(0, 10, n).astype(dtype)
+                if dtype is np.complex128:
+                    xg = xg + 1j * rng.normal(0, 10, n)
+                xg = comm.bcast(xg, 0)
+                Fop = pm.MPIFirstDerivative(dims, sampling=h, kind=kind, edge=edge, order=order, dtype=dtype)
+                D = o.first_derivative_dense(dims[0], h, kind, edge, order)
+                X = xg.reshape(dims[0], -1)
+                for part in (pm.Partition.SCATTER, pm.Partition.BROADCAST):
+                    xd = pm.DistributedArray.to_dist(xg, partition=part)
+                    y, ya = Fop @ xd, Fop.H @ xd
+                    check(f"fd {dims} {kind}{order} {edge}", host(y.asarray()), (D @ X).ravel())
+                    check(f"fdH {dims} {kind}{order} {edge}", host(ya.asarray()), (D.T @ X).ravel())
+                try:
+                    refl = o.first_derivative(o.to_dist(xg, P), dims, h, kind, edge, order, False, dtype=dtype)
+                    check("fd per-rank", host((Fop @ pm.DistributedArray.to_dist(xg)).local_array), refl[rank])
+                except (ValueError, IndexError):
+                    pass
+                u = pm.DistributedArray.to_dist(comm.bcast(rng.normal(0, 10, n), 0).astype(dtype))
+                v = pm.DistributedArray.to_dist(comm.bcast(rng.normal(0, 10, n), 0).astype(dtype))
+                assert pm.dottest(Fop, u, v)
+
+# ---- BlockDiag / VStack / HStack (test_blockdiag.py:24-71, test_stack.py:29-79) ---------------------
+for ny, nx in [(101, 101), (301, 101)]:
+    for dtype in (np.float64, np.complex128):
+        blocks = [[((r + 1) * np.ones((ny, nx))).astype(dtype)] for r in range(P)]
+        BD = pm.MPIBlockDiag([pm.MatrixMult(blocks[rank][0])])
+        assert BD.shape == (P * ny, P * nx)
+        xd = pm.DistributedArray(global_shape=P * nx, dtype=dtype)
+        xd[:] = 1.0
+        y = BD @ xd
+        check("bd", host(y.local_array), (rank + 1) * nx * np.ones(ny), 1e-13, 0)
+        yd = pm.DistributedArray(global_shape=P * ny, dtype=dtype)
+        yd[:] = 1.0
+        check("bdH", host((BD.H @ yd).local_array), (rank + 1) * ny * np.ones(nx), 1e-13, 0)
+        assert pm.dottest(BD, xd, yd)
+        VS = pm.MPIVStack([pm.MatrixMult(blocks[rank][0])])
+        xb = pm.DistributedArray(global_shape=nx, partition=pm.Partition.BROADCAST, dtype=dtype)
+        xb[:] = 1.0
+        check("vs", host((VS @ xb).local_array), (rank + 1) * nx * np.ones(ny), 1e-13, 0)
+        xr = VS.H @ yd
+        assert xr.partition is pm.Partition.BROADCAST
+        check("vsH", host(xr.local_array), sum(r + 1 for r in range(P)) * ny * np.ones(nx), 1e-13, 0)
+        # random blocks + un-aligned flat input (re-partition path) vs oracle
+        rb = [[comm.bcast(np.random.default_rng(7 + r).standard_normal((ny - r, nx)).astype(dtype), 0)] for r in range(P)]
+        BD2 = pm.MPIBlockDiag([pm.MatrixMult(rb[rank][0])])
+        xv = comm.bcast(np.random.default_rng(1).standard_normal(P * nx).astype(dtype), 0)
+        check("bd2", host((BD2 @ pm.DistributedArray.to_dist(xv)).local_array), o.blockdiag(rb, o.to_dist(xv, P))[rank])
+        yv = comm.bcast(np.random.default_rng(2).standard_normal(sum(ny - r for r in range(P))).astype(dtype), 0)
+        check("bd2H", host((BD2.H @ pm.DistributedArray.to_dist(yv)).local_array),
+              o.blockdiag(rb, o.to_dist(yv, P), adjoint=True)[rank])
+        VS2 = pm.MPIVStack([pm.MatrixMult(rb[rank][0])])
+        check("vs2H", host((VS2.H @ pm.DistributedArray.to_dist(yv)).local_array), o.vstack_rmatvec(rb, o.to_dist(yv, P)), 1e-11, 1e-11)
+
+# ---- MPIMatrixMult (square grids only, like the reference) -------------------------------------------
+Pp = math.isqrt(P)
+if Pp * Pp == P:
+    for (N, K, M, dtype) in [(64, 64, 64, np.float64), (37, 37, 37, np.float64), (50, 30, 40, np.float64),
+                             (22, 20, 16, np.complex128), (13, 14, 15, np.float32), (64, 48, Pp, np.float64)]:
+        A = np.arange(N * K, dtype=dtype).reshape(N, K)
+        X = np.arange(K * M, dtype=dtype).reshape(K, M)
+        if dtype is np.complex128:
+            A, X = A + 0.5j * A, X + 0.7j * X
+        rtol = np.finfo(dtype).resolution * 10
+        Yref = A.astype(np.complex128 if np.iscomplexobj(A) else np.float64) @ X
+        # SUMMA: 2-D tiles (test_matrixmult.py:108-127)
+        rs, cs = pm.local_block_split((N, K), rank, comm)
+        assert (rs, cs) == o.local_block_split((N, K), rank, P)
+        Aop = pm.MPIMatrixMult(A[rs, cs].copy(), M, kind="summa", dtype=dtype)
+        xs = pm.local_block_split((K, M), rank, comm)
+        sizes = [int(np.prod(X[o.local_block_split((K, M), r, P)].shape)) for r in range(P)]
+        xd = pm.DistributedArray(global_shape=K * M, local_shapes=sizes, dtype=dtype)
+        xd[:] = X[xs].ravel()
+        y = Aop @ xd
+        At = o.summa_tiles(A, P)
+        yo = o.summa_matvec(At, [t.flatten() for t in o.summa_tiles(X, P)], N, K, M, dtype=dtype)
+        check("summa", host(y.local_array), yo[rank], rtol, 0)
+        check("summa gather", host(pm.block_gather(y, (N, M), comm)), Yref, rtol, 0)
+        xa = Aop.H @ y
+        xo = o.summa_matvec(At, yo, N, K, M, dtype=dtype, adjoint=True)
+        check("summaH", host(xa.local_array), xo[rank], rtol * 10, 0)
+        # block variant (test_matrixmult.py:216-237)
+        blk, bc = int(math.ceil(N / Pp)), int(math.ceil(M / Pp))
+        ci, ri = rank % Pp, rank // Pp
+        Arow = A[ci * blk:min(N, (ci + 1) * blk)].copy()
+        Bop = pm.MPIMatrixMult(Arow, M, kind="block", dtype=dtype)
+        Xc = X[:, ri * bc:min(M, (ri + 1) * bc)]
+        ncs = [max(0, min(M, (r // Pp + 1) * bc) - (r // Pp) * bc) for r in range(P)]
+        xd = pm.DistributedArray(global_shape=K * sum(ncs), local_shapes=[K * c for c in ncs], dtype=dtype)
+        xd[:] = Xc.ravel()
+        yb = Bop @ xd
+        check("block", host(yb.local_array).reshape(N, -1), Yref[:, ri * bc:min(M, (ri + 1) * bc)], rtol, 0)
+        xb = Bop.H @ yb
+        check("blockH", host(xb.local_array).reshape(K, -1), (A.conj().T @ Yref)[:, ri * bc:min(M, (ri + 1) * bc)], rtol * 10, 0)
+
+# ---- MPIFredholm1 (test_fredholm.py) -------------------------------------------------------------------
+for nz in (5, 1):
+    for dtype in (np.float64, np.complex64):
+        cx = np.issubdtype(dtype, np.complexfloating)
+        nsl, nx, ny = 21, 4, 6
+        G = np.arange(nsl * nx * ny, dtype=np.float64).reshape(nsl, nx, ny)
+        G = (G - 1j * G) if cx else G
+        ext = [o.local_split((nsl,), P, r)[0] for r in range(P)]
+        if 1 in ext:
+            continue
+        off = np.cumsum([0] + ext)
+        G_loc = [G[off[r]:off[r + 1]] for r in range(P)]
+        Fr = pm.MPIFredholm1(G_loc[rank].astype(dtype), nz=nz, dtype=dtype)
+        xv = (np.ones((nsl, ny, nz)) + (1j if cx else 0)).astype(dtype)
+        xd = pm.DistributedArray.to_dist(xv.ravel(), partition=pm.Partition.BROADCAST)
+        y = Fr @ xd
+        refy = o.fredholm1(G_loc, xv.ravel().astype(G.dtype), nz)
+        check("fredholm", host(y.local_array), refy, 1e-5, 0)
+        check("fredholmH", host((Fr.H @ y).local_array), o.fredholm1(G_loc, refy, nz, adjoint=True), 1e-4, 0)
+
+# ---- CGLS on BlockDiag (test_solver.py:150-196) vs oracle at the same P ---------------------------------
+for ny, nx in [(11, 11), (31, 11)]:
+    blocks = []
+    for r in range(P):
+        A = np.ones((ny, nx)) * (r + 1)
+        blocks.append([A.T @ A + 1e-5 * np.eye(nx)])
+    Op = pm.MPIBlockDiag([pm.MatrixMult(blocks[rank][0])])
+    xt = comm.bcast(np.random.default_rng(42).normal(1, 10, P * nx), 0)
+    y = Op @ pm.DistributedArray.to_dist(xt)
+    xinv, istop, iit, r1, r2, cost = pm.cgls(Op, y, x0=pm.DistributedArray.to_dist(np.zeros(P * nx)), niter=nx, tol=1e-5)
+    mv = lambda v: o.SimArray(o.blockdiag(blocks, v.locs))                  # noqa: E731
+    rmv = lambda v: o.SimArray(o.blockdiag(blocks, v.locs, adjoint=True))   # noqa: E731
+    xo, istop_o, iit_o, r1o, r2o, cost_o = o.cgls(mv, rmv, mv(o.SimArray(o.to_dist(xt, P))),
+                                                  o.SimArray(o.to_dist(np.zeros(P * nx), P)), niter=nx, tol=1e-5)
+    assert (istop, iit) == (istop_o, iit_o)
+    check("cgls x", host(xinv.local_array), xo.locs[rank], 1e-6, 1e-8)
+    check("cgls cost", cost, cost_o, 1e-5, 1e-8)
+
+comm.Barrier()
+torch.cuda.synchronize()
+print(f"MULTI_WORKER_OK rank={rank} size={P}")

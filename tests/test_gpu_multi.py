@@ -1,0 +1,24 @@
+"""Multi-GPU parity: launches tests/multi_worker.py with one rank per GPU
+(2 ranks, and 4 when the box has them -- 4 also covers the square-grid
+MPIMatrixMult paths).  Skipped on a single-GPU box."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("nproc", [2, 4])
+def test_multi_rank_parity(nproc):
+    if torch.cuda.device_count() < nproc:
+        pytest.skip(f"needs {nproc} GPUs, box has {torch.cuda.device_count()}")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29700 + nproc),
+                        os.path.join(ROOT, "tests", "multi_worker.py")],
+                       capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, (r.stdout[-4000:] + r.stderr[-8000:])
+    assert r.stdout.count("MULTI_WORKER_OK") == nproc
