@@ -326,3 +326,39 @@ def test_batched_gemm_fredholm_kat(L, nz, dt):
     L.check(L.lib.b2_batched_gemm(L.ctx(), Gd.data_ptr(), yd.data_ptr(), xa.data_ptr(), nsl, nx, ny, nz, 1, code, L.stream()))
     refa = np.matmul(G.conj().transpose(0, 2, 1), yd.cpu().numpy().astype(G.dtype))
     np.testing.assert_allclose(xa.cpu().numpy(), refa, rtol=tol * 10)
+
+
+# --------------------------------------------------------------------------
+# bf16 tile product on tcgen05 tensor cores
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (128, 256, 256), (256, 512, 128), (1024, 1024, 1024),
+                                   (200, 264, 72), (8, 8, 8), (136, 40, 1000), (1, 16, 24), (384, 256, 64)])
+@pytest.mark.parametrize("op", [0, 1])
+def test_gemm_bf16_tcgen05(L, m, n, k, op):
+    torch.manual_seed(m * 7 + n * 3 + k + op)
+    A = (torch.randn((m, k) if op == 0 else (k, m), device="cuda") / 8).to(torch.bfloat16)
+    B = (torch.randn(k, n, device="cuda") / 8).to(torch.bfloat16)
+    Cm = torch.full((m, n), 7.0, device="cuda")
+    lda = A.shape[1]
+    L.check(L.lib.b2_gemm_bf16(L.ctx(), A.data_ptr(), lda, B.data_ptr(), n, Cm.data_ptr(), n, m, n, k, op, 0,
+                               L.stream()), "b2_gemm_bf16")
+    torch.cuda.synchronize()
+    A64 = A.double() if op == 0 else A.double().T
+    ref = A64 @ B.double()
+    # fp32 accumulation of exact bf16 products: error <= ~k * eps32 * sum|a||b|
+    bound = (A64.abs() @ B.double().abs()) * (k * 6e-8) + 1e-6
+    err = (Cm.double() - ref).abs()
+    assert bool((err <= bound).all()), f"max err {err.max().item()} at {m},{n},{k},{op}"
+    # accumulate into C
+    L.check(L.lib.b2_gemm_bf16(L.ctx(), A.data_ptr(), lda, B.data_ptr(), n, Cm.data_ptr(), n, m, n, k, op, 1,
+                               L.stream()), "b2_gemm_bf16")
+    err = (Cm.double() - 2 * ref).abs()
+    assert bool((err <= 2 * bound + 1e-5).all())
+
+
+def test_gemm_bf16_alignment_error_is_loud(L):
+    A = torch.zeros(8, 12, device="cuda", dtype=torch.bfloat16)
+    B = torch.zeros(12, 8, device="cuda", dtype=torch.bfloat16)
+    Cm = torch.zeros(8, 8, device="cuda")
+    rc = L.lib.b2_gemm_bf16(L.ctx(), A.data_ptr(), 12, B.data_ptr(), 8, Cm.data_ptr(), 8, 8, 8, 12, 0, 0, L.stream())
+    assert rc == 2006

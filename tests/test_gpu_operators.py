@@ -313,3 +313,27 @@ def test_cgls_config3_single_block_fp32(pm):
     rel = np.linalg.norm(host(xinv.asarray()) - xo.asarray()) / np.linalg.norm(xo.asarray())
     assert rel < 1e-5, rel
     assert np.linalg.norm(host(xinv.asarray()) - xt) / np.linalg.norm(xt) < 1e-5
+
+
+# ---- MPIMatrixMult bf16 -> fp32 (BASELINE config 4, reduced size) --------------------------------
+@pytest.mark.parametrize("kind", ["summa", "block"])
+@pytest.mark.parametrize("M", [1, 256])
+def test_matrixmult_bf16(pm, kind, M):
+    N = K = 1024
+    A = (np.random.default_rng(1).standard_normal((N, K)) / 181).astype(np.float32)
+    At = torch.as_tensor(A).to(torch.bfloat16)
+    X = np.random.default_rng(2).standard_normal((K, M)).astype(np.float32)
+    Xb = torch.as_tensor(X).to(torch.bfloat16).float().numpy() if M > 1 else X
+    Aop = pm.MPIMatrixMult(At, M, kind=kind, dtype="bfloat16")
+    x = pm.DistributedArray.to_dist(X.ravel())
+    y = Aop @ x
+    A64 = At.double().numpy()
+    ref = A64 @ Xb.astype(np.float64)
+    scale = np.abs(A64) @ np.abs(Xb.astype(np.float64))
+    err = np.abs(host(y.asarray()).reshape(N, M) - ref)
+    assert np.all(err <= scale * K * 6e-8 + 1e-6)
+    ya = Aop.H @ y
+    yb = torch.as_tensor(host(y.asarray()).reshape(N, M)).to(torch.bfloat16).double().numpy() if M > 1 else host(y.asarray()).reshape(N, M).astype(np.float64)
+    refa = A64.T @ yb
+    erra = np.abs(host(ya.asarray()).reshape(K, M) - refa)
+    assert np.all(erra <= (np.abs(A64.T) @ np.abs(yb)) * N * 6e-8 + 1e-6)
