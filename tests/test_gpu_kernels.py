@@ -332,7 +332,7 @@ def test_batched_gemm_fredholm_kat(L, nz, dt):
 # bf16 tile product on tcgen05 tensor cores
 # --------------------------------------------------------------------------
 @pytest.mark.parametrize("m,n,k", [(128, 256, 64), (128, 256, 256), (256, 512, 128), (1024, 1024, 1024),
-                                   (200, 264, 72), (8, 8, 8), (136, 40, 1000), (1, 16, 24), (384, 256, 64)])
+                                   (200, 264, 72), (8, 8, 8), (136, 40, 1000), (8, 16, 24), (384, 256, 64)])
 @pytest.mark.parametrize("op", [0, 1])
 def test_gemm_bf16_tcgen05(L, m, n, k, op):
     torch.manual_seed(m * 7 + n * 3 + k + op)
