@@ -1,0 +1,246 @@
+"""Generate golden fixtures by running the REAL reference (/root/reference,
+imported unmodified) under the in-process MPI shim in tests/golden/refshim/.
+
+    python tests/golden/make_golden.py            # writes tests/golden/reference_golden.npz
+
+Runs only in the build container (the GPU box has no /root/reference); the
+.npz it writes is committed and is what tests/test_golden.py checks the oracle
+and the CUDA path against.  Third-party ``pylops`` is absent from the image:
+its only arithmetic on this path (the dense block ``A @ x``) is restated in
+refshim/pylops; mpi4py is replaced by threads.  Everything else -- partition
+bookkeeping, @reshaped, ghost cells, the stencils, BlockDiag/VStack/MatrixMult/
+Fredholm1, dot/norm, CGLS, dottest -- is the reference's own code.
+"""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("PYLOPS_MPI_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "refshim"))
+
+
+def load_reference():
+    pkg = types.ModuleType("pylops_mpi")
+    pkg.__path__ = [os.path.join(REF, "pylops_mpi")]
+    sys.modules["pylops_mpi"] = pkg
+    da = importlib.import_module("pylops_mpi.DistributedArray")
+    pkg.DistributedArray, pkg.Partition = da.DistributedArray, da.Partition
+    pkg.StackedDistributedArray = da.StackedDistributedArray
+    lo = importlib.import_module("pylops_mpi.LinearOperator")
+    pkg.MPILinearOperator, pkg.asmpilinearoperator = lo.MPILinearOperator, lo.asmpilinearoperator
+    slo = importlib.import_module("pylops_mpi.StackedLinearOperator")
+    pkg.MPIStackedLinearOperator = slo.MPIStackedLinearOperator
+    # sub-packages: register bare namespaces so their __init__ (which pulls in operators that need
+    # more of third-party pylops than this path uses) is not executed
+    for sub in ("basicoperators", "signalprocessing", "optimization"):
+        m = types.ModuleType("pylops_mpi." + sub)
+        m.__path__ = [os.path.join(REF, "pylops_mpi", sub)]
+        sys.modules["pylops_mpi." + sub] = m
+        setattr(pkg, sub, m)
+    mods = {}
+    for name in ("basicoperators.FirstDerivative", "basicoperators.BlockDiag", "basicoperators.VStack",
+                 "basicoperators.MatrixMult", "signalprocessing.Fredholm1", "optimization.cls_basic",
+                 "utils.dottest"):
+        mods[name.split(".")[-1]] = importlib.import_module("pylops_mpi." + name)
+    return pkg, mods
+
+
+def main():
+    from mpi4py import MPI
+    import pylops
+    pkg, mods = load_reference()
+    DA, Partition = pkg.DistributedArray, pkg.Partition
+    FD = mods["FirstDerivative"].MPIFirstDerivative
+    BD = mods["BlockDiag"].MPIBlockDiag
+    VS = mods["VStack"].MPIVStack
+    MM = mods["MatrixMult"]
+    FR = mods["Fredholm1"].MPIFredholm1
+    CGLS = mods["cls_basic"].CGLS
+    dottest = mods["dottest"].dottest
+    out = {}
+
+    def put(key, val):
+        out[key] = np.asarray(val)
+
+    # ---- DistributedArray: partition, dot, norm, masks, ghost cells -----------------------------
+    def t_array(rank, P, shape, axis):
+        rng = np.random.default_rng(42)
+        a = rng.normal(100, 100, shape)
+        b = rng.normal(300, 300, shape)
+        A = DA.to_dist(a, axis=axis)
+        B = DA.to_dist(b, axis=axis)
+        res = {"local_shape": A.local_shape, "local_shapes": A.local_shapes, "dot": A.dot(B), "vdot": A.dot(B, vdot=True),
+               "add": (A + B).asarray(), "mul": (A * B).asarray()}
+        for o_ in (1, 2, np.inf, -np.inf, 0, 3):
+            res[f"norm{o_}"] = A.norm(o_)
+        Bc = DA.to_dist(a, partition=Partition.BROADCAST)
+        res["bdot"] = Bc.dot(Bc)
+        if P >= 2:
+            mask = [r % 2 for r in range(P)]
+            Am = DA.to_dist(a, axis=axis, mask=mask)
+            res["mdot"] = Am.dot(Am)
+            res["mnorm"] = Am.norm(1)
+        if axis == 0 and min(A.local_shapes)[0] >= 2:
+            res["ghost"] = A.add_ghost_cells(cells_front=2, cells_back=1)
+        return res
+
+    for P in (1, 2, 3, 4):
+        for shape, axis in (((50, 51), 1), ((51, 50), 0), ((20, 21, 11), 1), ((600,), 0)):
+            for r, res in enumerate(MPI.run_world(P, t_array, P, shape, axis)):
+                for k, v in res.items():
+                    put(f"array/P{P}/{shape}/ax{axis}/r{r}/{k}", v)
+
+    # ---- MPIFirstDerivative ---------------------------------------------------------------------------
+    def t_fd(rank, dims, h, kind, edge, order, dtype):
+        rng = np.random.default_rng(7)
+        n = int(np.prod(dims))
+        x = rng.normal(0, 10, n).astype(dtype)
+        if np.issubdtype(dtype, np.complexfloating):
+            x = x + 1j * rng.normal(0, 10, n)
+        Fop = FD(dims, sampling=h, kind=kind, edge=edge, order=order, dtype=dtype)
+        xd = DA.to_dist(x)
+        y = Fop @ xd
+        ya = Fop.H @ xd
+        u = DA.to_dist(rng.normal(0, 10, n).astype(dtype))
+        v = DA.to_dist(rng.normal(0, 10, n).astype(dtype))
+        return {"x": x, "y_local": y.local_array, "ya_local": ya.local_array, "dottest": dottest(Fop, u, v)}
+
+    for P in (1, 2, 3, 4):
+        for dims, h in (((11, 21), 1.0), ((13,), 1.0), ((30, 17), 0.4), ((29, 5, 3), 0.4), ((600,), 1.0)):
+            for kind, order in (("forward", 3), ("backward", 3), ("centered", 3), ("centered", 5)):
+                for edge in (False, True):
+                    for dtype in (np.float64, np.complex128):
+                        key = f"fd/P{P}/{dims}/h{h}/{kind}{order}/e{int(edge)}/{np.dtype(dtype).name}"
+                        try:
+                            res = MPI.run_world(P, t_fd, dims, h, kind, edge, order, dtype)
+                        except (ValueError, IndexError) as exc:
+                            put(key + "/reference_raises", type(exc).__name__)
+                            continue
+                        put(key + "/x", res[0]["x"])
+                        for r, d in enumerate(res):
+                            put(key + f"/r{r}/y", d["y_local"])
+                            put(key + f"/r{r}/ya", d["ya_local"])
+                            assert d["dottest"]
+
+    # config 1 (README.md:73-94) incl. dottest + cgls(niter=10)
+    def t_config1(rank):
+        x = np.zeros((11, 21))
+        x[5, 10] = 1.0
+        Fop = FD((11, 21), dtype=np.float64)
+        xd = DA.to_dist(x.ravel())
+        y = Fop @ xd
+        x0 = DA(global_shape=231, local_shapes=y.local_shapes)
+        x0[:] = 0
+        solver = CGLS(Fop)
+        xinv, istop, iit, r1, r2, cost = solver.solve(y, x0, niter=10, tol=0.0)
+        return {"y": y.asarray().reshape(11, 21), "xinv": xinv.asarray(), "cost": cost, "iit": iit, "istop": istop}
+
+    res = MPI.run_world(2, t_config1)[0]
+    for k, v in res.items():
+        put(f"config1/{k}", v)
+
+    # ---- BlockDiag / VStack / CGLS (test_blockdiag.py, test_stack.py, test_solver.py) ----------------------
+    def t_stack(rank, P, ny, nx, dtype):
+        blocks = [np.random.default_rng(100 + r).standard_normal((ny - r, nx)).astype(dtype) for r in range(P)]
+        if np.issubdtype(dtype, np.complexfloating):
+            blocks = [b + 1j * np.random.default_rng(200 + r).standard_normal(b.shape) for r, b in enumerate(blocks)]
+        Op = pylops.MatrixMult(blocks[rank], dtype=dtype)
+        BDop = BD([Op])
+        xg = np.random.default_rng(1).standard_normal(P * nx).astype(dtype)
+        yg = np.random.default_rng(2).standard_normal(sum(ny - r for r in range(P))).astype(dtype)
+        y = BDop @ DA.to_dist(xg)
+        xa = BDop.H @ DA.to_dist(yg)
+        VSop = VS([Op])
+        xb = DA.to_dist(xg[:nx], partition=Partition.BROADCAST)
+        yv = VSop @ xb
+        xv = VSop.H @ DA.to_dist(yg)
+        # cgls on the normal-equation style block of test_solver.py:150-196
+        A = np.ones((ny, nx), dtype=dtype) * (rank + 1)
+        blk = A.conj().T @ A + 1e-5 * np.eye(nx, dtype=dtype)
+        Sop = BD([pylops.MatrixMult(blk, dtype=dtype)])
+        xt = np.random.default_rng(42).normal(1, 10, P * nx).astype(dtype)
+        yy = Sop @ DA.to_dist(xt)
+        x0 = DA.to_dist(np.zeros(P * nx, dtype=dtype))
+        xinv, istop, iit, r1, r2, cost = CGLS(Sop).solve(yy, x0, niter=nx, tol=1e-5)
+        return {"bd_y": y.local_array, "bd_xa": xa.local_array, "vs_y": yv.local_array, "vs_x": xv.local_array,
+                "cgls_x": xinv.local_array, "cgls_cost": cost, "cgls_iit": iit, "cgls_istop": istop,
+                "cgls_r1": r1, "cgls_r2": r2}
+
+    for P in (1, 2, 4):
+        for ny, nx in ((11, 11), (31, 11)):
+            for dtype in (np.float64, np.complex128):
+                for r, res in enumerate(MPI.run_world(P, t_stack, P, ny, nx, dtype)):
+                    for k, v in res.items():
+                        put(f"stack/P{P}/{ny}x{nx}/{np.dtype(dtype).name}/r{r}/{k}", v)
+
+    # ---- MPIMatrixMult block + summa (test_matrixmult.py) ---------------------------------------------------
+    def t_mm(rank, P, N, K, M, dtype, kind):
+        import math
+        comm = MPI.COMM_WORLD
+        A = np.arange(N * K, dtype=dtype).reshape(N, K)
+        X = np.arange(K * M, dtype=dtype).reshape(K, M)
+        if np.issubdtype(dtype, np.complexfloating):
+            A, X = A + 0.5j * A, X + 0.7j * X
+        Pp = math.isqrt(P)
+        if kind == "summa":
+            rs, cs = MM.local_block_split((N, K), rank, comm)
+            Aop = MM.MPIMatrixMult(A[rs, cs].copy(), M, kind="summa", dtype=dtype)
+            xs = MM.local_block_split((K, M), rank, comm)
+            sizes = comm.allgather(int(np.prod(X[xs].shape)))
+            xd = DA(global_shape=K * M, local_shapes=sizes, dtype=dtype)
+            xd[:] = X[xs].ravel()
+        else:
+            blk, bc = int(math.ceil(N / Pp)), int(math.ceil(M / Pp))
+            ci, ri = rank % Pp, rank // Pp
+            Aop = MM.MPIMatrixMult(A[ci * blk:min(N, (ci + 1) * blk)].copy(), M, kind="block", dtype=dtype)
+            Xc = X[:, ri * bc:min(M, (ri + 1) * bc)]
+            ncs = comm.allgather(Xc.shape[1])
+            xd = DA(global_shape=K * sum(ncs), local_shapes=[K * c for c in ncs], dtype=dtype)
+            xd[:] = Xc.ravel()
+        y = Aop @ xd
+        xa = Aop.H @ y
+        return {"y": y.local_array, "xa": xa.local_array}
+
+    for P in (1, 4, 9):
+        for (N, K, M, dtype) in ((64, 64, 64, np.float64), (37, 37, 37, np.float64), (50, 30, 40, np.float64),
+                                 (22, 20, 16, np.complex128), (13, 14, 15, np.float32)):
+            for kind in ("summa", "block"):
+                for r, res in enumerate(MPI.run_world(P, t_mm, P, N, K, M, dtype, kind)):
+                    for k, v in res.items():
+                        put(f"mm/P{P}/{N}x{K}x{M}/{np.dtype(dtype).name}/{kind}/r{r}/{k}", v)
+
+    # ---- MPIFredholm1 (test_fredholm.py) ------------------------------------------------------------------------
+    def t_fr(rank, P, nz, dtype, saveGt, usematmul):
+        nsl, nx, ny = 21, 4, 6
+        rng = np.random.default_rng(5)
+        G = rng.standard_normal((nsl, nx, ny))
+        if np.issubdtype(dtype, np.complexfloating):
+            G = G + 1j * rng.standard_normal((nsl, nx, ny))
+        G = G.astype(dtype)
+        x = np.random.default_rng(6).standard_normal(nsl * ny * nz).astype(dtype)
+        ext = [nsl // P + (1 if r < nsl % P else 0) for r in range(P)]
+        off = np.cumsum([0] + ext)
+        Fop = FR(G[off[rank]:off[rank + 1]], nz=nz, saveGt=saveGt, usematmul=usematmul, dtype=dtype)
+        y = Fop @ DA.to_dist(x, partition=Partition.BROADCAST)
+        xa = Fop.H @ y
+        return {"y": y.local_array, "xa": xa.local_array}
+
+    for P in (1, 2, 3):
+        for nz in (5, 1):
+            for dtype in (np.float64, np.complex128):
+                for saveGt, usematmul in ((True, True), (False, False)):
+                    res = MPI.run_world(P, t_fr, P, nz, dtype, saveGt, usematmul)[0]
+                    for k, v in res.items():
+                        put(f"fredholm/P{P}/nz{nz}/{np.dtype(dtype).name}/s{int(saveGt)}m{int(usematmul)}/{k}", v)
+
+    path = os.path.join(HERE, "reference_golden.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")
+
+
+if __name__ == "__main__":
+    main()
