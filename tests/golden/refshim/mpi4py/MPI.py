@@ -4,7 +4,7 @@ import threading
 import numpy as np
 
 _tl = threading.local()
-_lock = threading.Lock()
+_lock = threading.RLock()
 _next_id = [1]
 
 
@@ -32,6 +32,17 @@ def _reduce(vals, op):
     if op is MIN:
         return np.minimum.reduce(vals) if isinstance(vals[0], np.ndarray) else min(vals)
     raise NotImplementedError(op)
+
+
+def _mem(a):
+    """flat view of a contiguous array in MEMORY order (MPI moves raw bytes: an F-ordered
+    buffer such as ``A.T.conj()`` travels in its own layout)"""
+    a = np.asarray(a)
+    if a.flags.c_contiguous:
+        return a.reshape(-1)
+    if a.flags.f_contiguous:
+        return a.T.reshape(-1)
+    raise ValueError("MPI buffers must be contiguous")
 
 
 def _buf(spec):
@@ -97,27 +108,25 @@ class Comm:
 
     # -- buffer collectives --------------------------------------------------------
     def Allgather(self, sendbuf, recvbuf):
-        parts = self.allgather(np.array(_buf(sendbuf), copy=True))
-        rb = _buf(recvbuf)
-        rb.reshape(-1)[:] = np.concatenate([p.reshape(-1) for p in parts])
+        parts = self.allgather(np.array(_mem(_buf(sendbuf)), copy=True))
+        _mem(_buf(recvbuf))[:] = np.concatenate(parts)
 
     def Allgatherv(self, sendbuf, recvspec):
-        parts = self.allgather(np.array(_buf(sendbuf), copy=True))
+        parts = self.allgather(np.array(_mem(_buf(sendbuf)), copy=True))
         rb, counts, displs = recvspec[0], recvspec[1], recvspec[2]
-        flat = rb.reshape(-1)
+        flat = _mem(rb)
         for p, c, d in zip(parts, counts, displs):
-            flat[d:d + c] = p.reshape(-1)[:c]
+            flat[d:d + c] = p[:c]
 
     def Allreduce(self, sendbuf, recvbuf, op=SUM):
-        parts = self.allgather(np.array(_buf(sendbuf), copy=True))
-        red = _reduce([p.reshape(-1) for p in parts], op)
-        _buf(recvbuf).reshape(-1)[:] = red
+        parts = self.allgather(np.array(_mem(_buf(sendbuf)), copy=True))
+        _mem(_buf(recvbuf))[:] = _reduce(parts, op)
 
     def Bcast(self, buf, root=0):
         b = _buf(buf)
-        val = self.allgather(np.array(b, copy=True) if self.Get_rank() == root else None)[root]
+        val = self.allgather(np.array(_mem(b), copy=True) if self.Get_rank() == root else None)[root]
         if self.Get_rank() != root:
-            b[...] = val.reshape(b.shape)
+            _mem(b)[:] = val
 
     # -- point to point ---------------------------------------------------------------
     def _q(self, src, dst, tag):
@@ -131,12 +140,12 @@ class Comm:
         return self._q(source, self.Get_rank(), tag).get(timeout=60)
 
     def Send(self, buf, dest, tag=0):
-        self._q(self.Get_rank(), dest, tag).put(np.array(_buf(buf), copy=True))
+        self._q(self.Get_rank(), dest, tag).put(np.array(_mem(_buf(buf)), copy=True))
 
     def Recv(self, buf, source=0, tag=0):
         b = _buf(buf)
         val = self._q(source, self.Get_rank(), tag).get(timeout=60)
-        b.reshape(-1)[:] = val.reshape(-1)
+        _mem(b)[:val.size] = val
 
     def Sendrecv(self, sendbuf, dest, sendtag=0, recvbuf=None, source=0, recvtag=0):
         self.Send(sendbuf, dest, sendtag)

@@ -1,0 +1,305 @@
+"""Golden-vector tests.  tests/golden/reference_golden.npz was produced by the
+REAL reference code (imported from /root/reference under the in-process MPI shim,
+tests/golden/make_golden.py).  Here:
+  * CPU (not gpu): the oracle must reproduce every fixture -> the oracle is pinned;
+  * GPU: the CUDA path (world size 1) must reproduce the gathered fixtures.
+"""
+import ast
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import pylops_mpi_oracle as o
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "reference_golden.npz"), allow_pickle=False)
+KEYS = list(GOLD.keys())
+
+
+def cases(prefix, depth):
+    """distinct key prefixes with `depth` components under `prefix`"""
+    seen = []
+    for k in KEYS:
+        if k.startswith(prefix + "/"):
+            c = "/".join(k.split("/")[:depth])
+            if c not in seen:
+                seen.append(c)
+    return seen
+
+
+def ranks_of(case, name):
+    out = []
+    r = 0
+    while f"{case}/r{r}/{name}" in GOLD:
+        out.append(GOLD[f"{case}/r{r}/{name}"])
+        r += 1
+    return out
+
+
+FD_CASES = cases("fd", 7)
+KIND = re.compile(r"([a-z]+)(\d)")
+
+
+def parse_fd(case):
+    _, P, dims, h, ko, e, dt = case.split("/")
+    kind, order = KIND.match(ko).groups()
+    return int(P[1:]), ast.literal_eval(dims), float(h[1:]), kind, int(order), bool(int(e[1:])), np.dtype(dt)
+
+
+def test_fixture_inventory():
+    assert len(FD_CASES) == 4 * 5 * 4 * 2 * 2
+    assert len(cases("array", 4)) == 16 and len(cases("stack", 4)) == 12
+    assert len(cases("mm", 5)) == 30 and len(cases("fredholm", 5)) == 24
+    assert "config1/y" in GOLD
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle vs the real reference (CPU)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", FD_CASES)
+def test_oracle_first_derivative(case):
+    P, dims, h, kind, order, edge, dt = parse_fd(case)
+    if case + "/reference_raises" in GOLD:
+        with pytest.raises((ValueError, IndexError)):
+            x = np.zeros(int(np.prod(dims)), dtype=dt)
+            o.first_derivative(o.to_dist(x, P), dims, h, kind, edge, order, False, dtype=dt)
+            o.first_derivative(o.to_dist(x, P), dims, h, kind, edge, order, True, dtype=dt)
+        return
+    x = GOLD[case + "/x"]
+    y = o.first_derivative(o.to_dist(x, P), dims, h, kind, edge, order, False, dtype=dt)
+    ya = o.first_derivative(o.to_dist(x, P), dims, h, kind, edge, order, True, dtype=dt)
+    for r, (gy, gya) in enumerate(zip(ranks_of(case, "y"), ranks_of(case, "ya"))):
+        np.testing.assert_array_equal(y[r], gy.ravel())       # same NumPy ops -> bit-exact
+        np.testing.assert_array_equal(ya[r], gya.ravel())
+
+
+def test_oracle_config1():
+    x = np.zeros((11, 21))
+    x[5, 10] = 1.0
+    y = np.concatenate(o.first_derivative(o.to_dist(x.ravel(), 2), (11, 21)))
+    assert np.array_equal(y.reshape(11, 21), GOLD["config1/y"])
+    mv = lambda a: o.SimArray(o.first_derivative(a.locs, (11, 21)))                   # noqa: E731
+    rmv = lambda a: o.SimArray(o.first_derivative(a.locs, (11, 21), adjoint=True))    # noqa: E731
+    xo, istop, iit, r1, r2, cost = o.cgls(mv, rmv, mv(o.SimArray(o.to_dist(x.ravel(), 2))),
+                                          o.SimArray([np.zeros(126), np.zeros(105)]), niter=10, tol=0.0)
+    assert iit == int(GOLD["config1/iit"]) and istop == int(GOLD["config1/istop"])
+    np.testing.assert_allclose(cost, GOLD["config1/cost"], rtol=1e-12, atol=1e-30)
+    np.testing.assert_allclose(xo.asarray(), GOLD["config1/xinv"], rtol=1e-12, atol=1e-30)
+
+
+@pytest.mark.parametrize("case", cases("array", 4))
+def test_oracle_distributed_array(case):
+    _, P, shape, ax = case.split("/")
+    P, shape, axis = int(P[1:]), ast.literal_eval(shape), int(ax[2:])
+    rng = np.random.default_rng(42)
+    a = rng.normal(100, 100, shape)
+    b = rng.normal(300, 300, shape)
+    al, bl = o.to_dist(a, P, axis=axis), o.to_dist(b, P, axis=axis)
+    mask = [r % 2 for r in range(P)]
+    for r in range(P):
+        g = lambda n: GOLD[f"{case}/r{r}/{n}"]   # noqa: E731
+        assert tuple(g("local_shape")) == o.local_split(shape, P, r, o.SCATTER, axis)
+        assert [tuple(s) for s in g("local_shapes")] == o.local_shapes(shape, P, o.SCATTER, axis)
+        np.testing.assert_allclose(o.dot(al, bl)[r], g("dot"), rtol=1e-14)
+        np.testing.assert_allclose(o.dot(al, bl, vdot=True)[r], g("vdot"), rtol=1e-14)
+        np.testing.assert_array_equal(a + b, g("add"))
+        for o_ in (1, 2, np.inf, -np.inf, 0, 3):
+            np.testing.assert_allclose(o.norm(al, o_)[r], g(f"norm{o_}"), rtol=1e-14)
+        np.testing.assert_allclose(o.dot([a] * P, [a] * P, partition=o.BROADCAST)[r], g("bdot"), rtol=1e-14)
+        if P >= 2:
+            np.testing.assert_allclose(o.dot(al, al, mask=mask)[r], g("mdot"), rtol=1e-14)
+            np.testing.assert_allclose(o.norm(al, 1, mask=mask)[r], g("mnorm"), rtol=1e-14)
+        if f"{case}/r{r}/ghost" in GOLD:
+            np.testing.assert_array_equal(o.add_ghost_cells(al, 0, [2] * P, [1] * P)[r], g("ghost"))
+
+
+def stack_blocks(P, ny, nx, dtype):
+    blocks = [np.random.default_rng(100 + r).standard_normal((ny - r, nx)).astype(dtype) for r in range(P)]
+    if np.issubdtype(dtype, np.complexfloating):
+        blocks = [b + 1j * np.random.default_rng(200 + r).standard_normal(b.shape) for r, b in enumerate(blocks)]
+    xg = np.random.default_rng(1).standard_normal(P * nx).astype(dtype)
+    yg = np.random.default_rng(2).standard_normal(sum(ny - r for r in range(P))).astype(dtype)
+    return blocks, xg, yg
+
+
+@pytest.mark.parametrize("case", cases("stack", 4))
+def test_oracle_blockdiag_vstack_cgls(case):
+    _, P, shp, dt = case.split("/")
+    P, (ny, nx), dtype = int(P[1:]), tuple(int(v) for v in shp.split("x")), np.dtype(dt)
+    blocks, xg, yg = stack_blocks(P, ny, nx, dtype)
+    bl = [[b] for b in blocks]
+    y = o.blockdiag(bl, o.to_dist(xg, P))
+    xa = o.blockdiag(bl, o.to_dist(yg, P), adjoint=True)
+    yv = o.vstack_matvec(bl, xg[:nx])
+    xv = o.vstack_rmatvec(bl, o.to_dist(yg, P))
+    sblocks = []
+    for r in range(P):
+        A = np.ones((ny, nx), dtype=dtype) * (r + 1)
+        sblocks.append([A.conj().T @ A + 1e-5 * np.eye(nx, dtype=dtype)])
+    xt = np.random.default_rng(42).normal(1, 10, P * nx).astype(dtype)
+    mv = lambda v: o.SimArray(o.blockdiag(sblocks, v.locs))                  # noqa: E731
+    rmv = lambda v: o.SimArray(o.blockdiag(sblocks, v.locs, adjoint=True))   # noqa: E731
+    xo, istop, iit, r1, r2, cost = o.cgls(mv, rmv, mv(o.SimArray(o.to_dist(xt, P))),
+                                          o.SimArray(o.to_dist(np.zeros(P * nx, dtype=dtype), P)), niter=nx, tol=1e-5)
+    for r in range(P):
+        g = lambda n: GOLD[f"{case}/r{r}/{n}"]   # noqa: E731
+        np.testing.assert_allclose(y[r], g("bd_y"), rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(xa[r], g("bd_xa"), rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(yv[r], g("vs_y"), rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(xv, g("vs_x"), rtol=1e-12, atol=1e-12)
+        assert (iit, istop) == (int(g("cgls_iit")), int(g("cgls_istop")))
+        np.testing.assert_allclose(xo.locs[r], g("cgls_x"), rtol=1e-8, atol=1e-10)
+        np.testing.assert_allclose(cost, g("cgls_cost"), rtol=1e-7, atol=1e-12)
+        np.testing.assert_allclose([r1, r2], [g("cgls_r1"), g("cgls_r2")], rtol=1e-6, atol=1e-14)
+
+
+def mm_inputs(N, K, M, dtype):
+    A = np.arange(N * K, dtype=dtype).reshape(N, K)
+    X = np.arange(K * M, dtype=dtype).reshape(K, M)
+    if np.issubdtype(dtype, np.complexfloating):
+        A, X = A + 0.5j * A, X + 0.7j * X
+    return A, X
+
+
+@pytest.mark.parametrize("case", cases("mm", 5))
+def test_oracle_matrixmult(case):
+    _, P, shp, dt, kind = case.split("/")
+    P, (N, K, M), dtype = int(P[1:]), tuple(int(v) for v in shp.split("x")), np.dtype(dt)
+    A, X = mm_inputs(N, K, M, dtype)
+    Pp = math.isqrt(P)
+    rtol = 1e-5 if dtype == np.float32 else 1e-13
+    if kind == "summa":
+        At = o.summa_tiles(A, P)
+        y = o.summa_matvec(At, [t.flatten() for t in o.summa_tiles(X, P)], N, K, M, dtype=dtype)
+        xa = o.summa_matvec(At, y, N, K, M, dtype=dtype, adjoint=True)
+    else:
+        blk, bc = int(math.ceil(N / Pp)), int(math.ceil(M / Pp))
+        Arows = [A[(r % Pp) * blk:min(N, (r % Pp + 1) * blk)] for r in range(P)]
+        Xc = [X[:, (r // Pp) * bc:min(M, (r // Pp + 1) * bc)].flatten() for r in range(P)]
+        y = o.blockmm_matvec(Arows, Xc, N, K, M, dtype=dtype)
+        xa = o.blockmm_matvec(Arows, y, N, K, M, dtype=dtype, adjoint=True)
+    for r in range(P):
+        gy, gxa = GOLD[f"{case}/r{r}/y"], GOLD[f"{case}/r{r}/xa"]
+        np.testing.assert_allclose(y[r], gy, rtol=rtol)
+        if np.all(np.isfinite(gxa)):
+            np.testing.assert_allclose(xa[r], gxa, rtol=rtol * 10)
+
+
+def fredholm_inputs(nz, dtype):
+    nsl, nx, ny = 21, 4, 6
+    rng = np.random.default_rng(5)
+    G = rng.standard_normal((nsl, nx, ny))
+    if np.issubdtype(dtype, np.complexfloating):
+        G = G + 1j * rng.standard_normal((nsl, nx, ny))
+    x = np.random.default_rng(6).standard_normal(nsl * ny * nz).astype(dtype)
+    return G.astype(dtype), x
+
+
+@pytest.mark.parametrize("case", cases("fredholm", 5))
+def test_oracle_fredholm(case):
+    _, P, nz, dt, flags = case.split("/")
+    P, nz, dtype = int(P[1:]), int(nz[2:]), np.dtype(dt)
+    G, x = fredholm_inputs(nz, dtype)
+    ext = [o.local_split((21,), P, r)[0] for r in range(P)]
+    off = np.cumsum([0] + ext)
+    G_loc = [G[off[r]:off[r + 1]] for r in range(P)]
+    y = o.fredholm1(G_loc, x, nz)
+    np.testing.assert_allclose(y, GOLD[case + "/y"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(o.fredholm1(G_loc, y, nz, adjoint=True), GOLD[case + "/xa"], rtol=1e-12, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# CUDA path vs the real reference (GPU, world size 1: gathered fixtures)
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def pm():
+    import pylops_mpi_b200 as pm
+    return pm
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [c for c in FD_CASES if c + "/reference_raises" not in KEYS])
+def test_gpu_first_derivative_vs_reference(pm, case):
+    P, dims, h, kind, order, edge, dt = parse_fd(case)
+    x = GOLD[case + "/x"]
+    Fop = pm.MPIFirstDerivative(dims, sampling=h, kind=kind, edge=edge, order=order, dtype=dt)
+    xd = pm.DistributedArray.to_dist(x)
+    gy = np.concatenate([a.ravel() for a in ranks_of(case, "y")])
+    gya = np.concatenate([a.ravel() for a in ranks_of(case, "ya")])
+    np.testing.assert_allclose(host((Fop @ xd).asarray()), gy, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(host((Fop.H @ xd).asarray()), gya, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_gpu_config1_vs_reference(pm):
+    x = np.zeros((11, 21))
+    x[5, 10] = 1.0
+    Fop = pm.MPIFirstDerivative((11, 21), dtype=np.float64)
+    y = Fop @ pm.DistributedArray.to_dist(x.ravel())
+    assert np.array_equal(host(y.asarray()).reshape(11, 21), GOLD["config1/y"])
+    xinv, istop, iit, r1, r2, cost = pm.cgls(Fop, y, x0=pm.DistributedArray.to_dist(np.zeros(231)), niter=10, tol=0.0)
+    assert iit == int(GOLD["config1/iit"])
+    np.testing.assert_allclose(cost, GOLD["config1/cost"], rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(host(xinv.asarray()), GOLD["config1/xinv"], rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", cases("stack", 4))
+def test_gpu_blockdiag_vstack_cgls_vs_reference(pm, case):
+    _, P, shp, dt = case.split("/")
+    P, (ny, nx), dtype = int(P[1:]), tuple(int(v) for v in shp.split("x")), np.dtype(dt)
+    blocks, xg, yg = stack_blocks(P, ny, nx, dtype)
+    ops = [pm.MatrixMult(b) for b in blocks]                     # all P blocks on the one rank
+    BD = pm.MPIBlockDiag(ops)
+    g = lambda n: np.concatenate([GOLD[f"{case}/r{r}/{n}"] for r in range(P)])   # noqa: E731
+    np.testing.assert_allclose(host((BD @ pm.DistributedArray.to_dist(xg)).asarray()), g("bd_y"), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(host((BD.H @ pm.DistributedArray.to_dist(yg)).asarray()), g("bd_xa"), rtol=1e-12, atol=1e-12)
+    VS = pm.MPIVStack(ops)
+    xb = pm.DistributedArray.to_dist(xg[:nx], partition=pm.Partition.BROADCAST)
+    np.testing.assert_allclose(host((VS @ xb).asarray()), g("vs_y"), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(host((VS.H @ pm.DistributedArray.to_dist(yg)).asarray()), GOLD[f"{case}/r0/vs_x"],
+                               rtol=1e-11, atol=1e-11)
+    sops = []
+    for r in range(P):
+        A = np.ones((ny, nx), dtype=dtype) * (r + 1)
+        sops.append(pm.MatrixMult(A.conj().T @ A + 1e-5 * np.eye(nx, dtype=dtype)))
+    Sop = pm.MPIBlockDiag(sops)
+    xt = np.random.default_rng(42).normal(1, 10, P * nx).astype(dtype)
+    yy = Sop @ pm.DistributedArray.to_dist(xt)
+    xinv, istop, iit, r1, r2, cost = pm.cgls(Sop, yy, x0=pm.DistributedArray.to_dist(np.zeros(P * nx, dtype=dtype)),
+                                             niter=nx, tol=1e-5)
+    assert (iit, istop) == (int(GOLD[f"{case}/r0/cgls_iit"]), int(GOLD[f"{case}/r0/cgls_istop"]))
+    np.testing.assert_allclose(host(xinv.asarray()), g("cgls_x"), rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(cost, GOLD[f"{case}/r0/cgls_cost"], rtol=1e-5, atol=1e-8)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [c for c in cases("mm", 5) if c.split("/")[1] == "P1"])
+def test_gpu_matrixmult_vs_reference(pm, case):
+    _, P, shp, dt, kind = case.split("/")
+    (N, K, M), dtype = tuple(int(v) for v in shp.split("x")), np.dtype(dt)
+    A, X = mm_inputs(N, K, M, dtype)
+    Aop = pm.MPIMatrixMult(A, M, kind=kind, dtype=dtype)
+    y = Aop @ pm.DistributedArray.to_dist(X.ravel())
+    rtol = 1e-5 if dtype == np.float32 else 1e-13
+    np.testing.assert_allclose(host(y.asarray()), GOLD[f"{case}/r0/y"], rtol=rtol)
+    np.testing.assert_allclose(host((Aop.H @ y).asarray()), GOLD[f"{case}/r0/xa"], rtol=rtol * 10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", cases("fredholm", 5))
+def test_gpu_fredholm_vs_reference(pm, case):
+    _, P, nz, dt, flags = case.split("/")
+    nz, dtype = int(nz[2:]), np.dtype(dt)
+    G, x = fredholm_inputs(nz, dtype)
+    Fop = pm.MPIFredholm1(G, nz=nz, dtype=dtype)
+    y = Fop @ pm.DistributedArray.to_dist(x, partition=pm.Partition.BROADCAST)
+    np.testing.assert_allclose(host(y.asarray()), GOLD[case + "/y"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(host((Fop.H @ y).asarray()), GOLD[case + "/xa"], rtol=1e-11, atol=1e-11)
