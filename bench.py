@@ -35,6 +35,9 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
 
 import numpy as np  # noqa: E402
 
+# rank 0 must print exactly ONE JSON line on stdout: keep NCCL's banner / debug text off it
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROWS_PER_GPU = 32768
 NCOLS = 8192
 METRIC = "MPIFirstDerivative matvec GB/s (algorithmic bytes, centered-3 float32)"
@@ -432,6 +435,34 @@ def run_extras(pm, L, comm, peaks, args):
     except Exception as exc:
         out["gemm_bf16_8192^3"] = {"unavailable": repr(exc)}
     del Ab, bop
+    # config 4 through the operator: MPIMatrixMult SUMMA, 32768 x 32768 bf16 -> fp32, grid Pr x Pc
+    try:
+        grids = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
+        if size in grids:
+            Pr, Pc = grids[size]
+            Ng = Kg = 32768
+            ri, ci = divmod(rank, Pc)
+            At = (torch.randn(Ng // Pr, Kg // Pc, device="cuda",
+                              generator=torch.Generator(device="cuda").manual_seed(1 + rank)) / 181).to(torch.bfloat16)
+            for Mg in (4096, 1):
+                if Mg % Pc:
+                    Mg = Pc
+                Sop = pm.MPIMatrixMult(At, Mg, kind="summa", dtype="bfloat16", grid=(Pr, Pc))
+                sizes = [(Kg // Pr) * (Mg // Pc)] * size
+                xs = pm.DistributedArray(global_shape=Kg * Mg, local_shapes=sizes, dtype=np.float32)
+                xs.local_array.normal_()
+                ms = time_loop(lambda: Sop.matvec(xs), 5, 2, comm)
+                fl = 2.0 * Ng * Kg * Mg
+                key = f"summa_bf16_32768_M{Mg}_grid{Pr}x{Pc}"
+                out[key] = {"TF/s": fl * 5 / (ms * 1e-3) / 1e12, "ms": ms / 5,
+                            "frac_tensor_total": fl * 5 / (ms * 1e-3) / 1e12 / (size * peaks.get("bf16_tflops", 1590.0)),
+                            "GB/s_A": 2.0 * Ng * Kg * 5 / (ms * 1e-3) / 1e9}
+                ms = time_loop(lambda: Sop.rmatvec(Sop.matvec(xs)), 3, 1, comm)
+                out[key]["fwd+adj_ms"] = ms / 3
+                del Sop, xs
+            del At
+    except Exception as exc:
+        out["summa_bf16_32768"] = {"error": repr(exc)}
     # --- config 5: Fredholm1 (64 slices per GPU, 256 x 256 x 64, complex64) -------------------
     nsl, ns, nr, nv = 64, 256, 256, 64
     G = torch.randn(nsl, ns, nr, device="cuda", dtype=torch.complex64)

@@ -86,16 +86,36 @@ class MPIFirstDerivative(MPILinearOperator):
         _lib.check(_lib.lib.b2_first_derivative_halo(self._kind_code, self.order, int(adjoint),
                                                      C.byref(need_lo), C.byref(need_hi)),
                    "b2_first_derivative_halo")
-        lo = hi = None
-        n_lo = n_hi = 0
-        if x.size > 1:
-            plan = halo_plan(rows, x.rank, need_lo.value, need_hi.value)
-            n_lo, n_hi = plan["recv_lo"], plan["recv_hi"]
-            xr = torch.view_as_real(xl).reshape(nloc, ncols) if tdt.is_complex else xl.reshape(nloc, ncols)
-            if n_lo:
-                lo = torch.empty((n_lo, ncols), dtype=real_dt, device=xl.device)
-            if n_hi:
-                hi = torch.empty((n_hi, ncols), dtype=real_dt, device=xl.device)
+        y = DistributedArray(global_shape=x.global_shape, base_comm=x.base_comm,
+                             local_shapes=x.local_shapes, axis=x.axis, dtype=tdt)
+        if nloc == 0:
+            return y
+        xr = torch.view_as_real(xl).reshape(nloc, ncols) if tdt.is_complex else xl.reshape(nloc, ncols)
+        yl = y.local_array
+        yr = torch.view_as_real(yl).reshape(nloc, ncols) if tdt.is_complex else yl.reshape(nloc, ncols)
+        code = _lib.code(real_dt)
+        ctx = _lib.ctx()
+
+        def launch(r_begin, r_end, lo_t, lo_n, hi_t, hi_n):
+            """stencil on local rows [r_begin, r_end) with explicit halo tensors"""
+            if r_end <= r_begin:
+                return
+            _lib.check(_lib.lib.b2_first_derivative(
+                ctx, xr[r_begin:].data_ptr(), yr[r_begin:].data_ptr(),
+                lo_t.data_ptr() if lo_n else None, lo_n, hi_t.data_ptr() if hi_n else None, hi_n,
+                r_end - r_begin, ncols, row0 + r_begin, self.dims[0], self._kind_code, self.order,
+                int(self.edge), float(self.sampling), int(adjoint), code, _lib.stream()),
+                "b2_first_derivative")
+
+        if x.size == 1:
+            launch(0, nloc, None, 0, None, 0)
+            return y
+        plan = halo_plan(rows, x.rank, need_lo.value, need_hi.value)
+        n_lo, n_hi = plan["recv_lo"], plan["recv_hi"]
+        lo = torch.empty((n_lo, ncols), dtype=real_dt, device=xl.device) if n_lo else None
+        hi = torch.empty((n_hi, ncols), dtype=real_dt, device=xl.device) if n_hi else None
+
+        def exchange():
             with group(x.base_comm):
                 if plan["send_lo"]:
                     send(x.base_comm, xr[:plan["send_lo"]], x.rank - 1)
@@ -105,14 +125,40 @@ class MPIFirstDerivative(MPILinearOperator):
                     recv(x.base_comm, lo, x.rank - 1)
                 if n_hi:
                     recv(x.base_comm, hi, x.rank + 1)
-        y = DistributedArray(global_shape=x.global_shape, base_comm=x.base_comm,
-                             local_shapes=x.local_shapes, axis=x.axis, dtype=tdt)
-        if nloc:
-            _lib.check(_lib.lib.b2_first_derivative(
-                _lib.ctx(), xl.data_ptr(), y.local_array.data_ptr(),
-                lo.data_ptr() if lo is not None else None, n_lo,
-                hi.data_ptr() if hi is not None else None, n_hi,
-                nloc, ncols, row0, self.dims[0], self._kind_code, self.order, int(self.edge),
-                float(self.sampling), int(adjoint), _lib.code(real_dt), _lib.stream()),
-                "b2_first_derivative")
+
+        nl, nh = need_lo.value, need_hi.value
+        if nloc < 2 * (nl + nh) + 1:
+            # tiny block: exchange, then one launch
+            exchange()
+            launch(0, nloc, lo, n_lo, hi, n_hi)
+            return y
+        # overlap: halo rows travel over NVLink on a side stream while the interior rows (whose
+        # stencil never leaves this rank) are differentiated; two 1-2 row edge launches follow
+        main = torch.cuda.current_stream()
+        side = _side_stream(xl.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(ready)
+            exchange()
+            arrived = torch.cuda.Event()
+            arrived.record(side)
+        i0, i1 = n_lo, nloc - n_hi
+        launch(i0, i1, xr[i0 - min(nl, i0):] if i0 else None, min(nl, i0),
+               xr[i1:] if i1 < nloc else None, min(nh, nloc - i1))
+        main.wait_event(arrived)
+        if i0:
+            launch(0, i0, lo, n_lo, xr[i0:], min(nh, nloc - i0))
+        if i1 < nloc:
+            launch(i1, nloc, xr[i1 - min(nl, i1):], min(nl, i1), hi, n_hi)
         return y
+
+
+_SIDE = {}
+
+
+def _side_stream(device):
+    st = _SIDE.get(device)
+    if st is None:
+        st = _SIDE[device] = torch.cuda.Stream(device=device)
+    return st

@@ -209,17 +209,39 @@ class _MPIBlockMatrixMult(DistributedMixIn, MPILinearOperator):
 
 
 class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
-    """2-D SUMMA variant (MatrixMult.py:431-767) on a P' x P' grid."""
+    """2-D SUMMA (MatrixMult.py:431-767) on a Pr x Pc process grid.
+
+    The reference supports square grids only (`:566-567`); with the default ``grid=None`` this class
+    requires a square world and reproduces its tiling, padding (`:590-602`) and per-rank outputs exactly.
+    ``grid=(Pr, Pc)`` generalises to rectangular grids (BASELINE config 4 asks for 2 x 4): K is cut into
+    L = lcm(Pr, Pc) panels; an A tile owns L/Pc panel columns, an X tile L/Pr panel rows; round l
+    broadcasts A panel l along the grid row and X panel l along the grid column.
+
+    Pipelining: panel l+1 is broadcast on a side stream (double buffers) while the tile product of
+    panel l runs on the compute stream.  The adjoint needs, on grid row i, the panels
+    {A_{r,l} : r < Pr, l in X-tile i}; they are re-distributed ONCE at construction over the Pc ranks
+    of that row (same bytes as the A tile itself), replacing the reference's per-apply point-to-point
+    tile routing (`:742-763`) by row broadcasts.
+    """
 
     def __init__(self, A, M: int, saveAt: bool = False, base_comm=COMM_WORLD, dtype="float64",
-                 base_comm_nccl=None) -> None:
+                 base_comm_nccl=None, grid=None) -> None:
         base_comm = resolve(base_comm)
         rank, size = base_comm.Get_rank(), base_comm.Get_size()
-        self._P_prime = math.isqrt(size)
-        if self._P_prime * self._P_prime != size:
-            raise Exception(f"Number of processes must be a square number, provided {size} instead...")
-        P = self._P_prime
-        self._row_id, self._col_id = divmod(rank, P)
+        if grid is None:
+            self._P_prime = math.isqrt(size)
+            if self._P_prime * self._P_prime != size:
+                raise Exception(f"Number of processes must be a square number, provided {size} instead...")
+            Pr = Pc = self._P_prime
+        else:
+            Pr, Pc = int(grid[0]), int(grid[1])
+            if Pr * Pc != size:
+                raise Exception(f"grid {Pr}x{Pc} does not match {size} processes")
+            self._P_prime = Pr
+        self._Pr, self._Pc = Pr, Pc
+        self._L = Pr * Pc // math.gcd(Pr, Pc)
+        L = self._L
+        self._row_id, self._col_id = divmod(rank, Pc)
         self.base_comm = base_comm
         self._row_comm = base_comm.Split(color=self._row_id, key=self._col_id)
         self._col_comm = base_comm.Split(color=self._col_id, key=self._row_id)
@@ -227,117 +249,197 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
         self.N = int(self._col_comm.allreduce(int(A.shape[0])))
         self.K = int(self._row_comm.allreduce(int(A.shape[1])))
         self.M = int(M)
-        self._N_padded = math.ceil(self.N / P) * P
-        self._K_padded = math.ceil(self.K / P) * P
-        self._M_padded = math.ceil(self.M / P) * P
-        bn, bk = self._N_padded // P, self._K_padded // P
-        pr = (bn - A.shape[0]) if self._row_id == P - 1 else 0
-        pc = (bk - A.shape[1]) if self._col_id == P - 1 else 0
-        if pr > 0 or pc > 0:
-            A = torch.nn.functional.pad(A, (0, pc, 0, pr))
-        self.A = A.contiguous()
-        # transposed-grid copy of the tile: rank (i, j) keeps A_{j,i} so that the adjoint is a
-        # standard SUMMA with A^H row-broadcasts replaced by column-local products
-        self._At_src = self._exchange_transposed(self.A)
+        self._N_padded = math.ceil(self.N / Pr) * Pr
+        self._K_padded = math.ceil(self.K / L) * L
+        self._M_padded = math.ceil(self.M / Pc) * Pc
+        self._bn, self._bm = self._N_padded // Pr, self._M_padded // Pc
+        self._w = self._K_padded // L                       # panel width
+        self._pa, self._px = L // Pc, L // Pr               # panels per A tile / per X tile
+        bkA = self._w * self._pa
+        if A.shape[0] > self._bn or A.shape[1] > bkA:
+            raise ValueError(f"local A tile {tuple(A.shape)} larger than the grid tile ({self._bn}, {bkA})")
+        if A.shape[0] != self._bn or A.shape[1] != bkA:
+            A = torch.nn.functional.pad(A, (0, bkA - A.shape[1], 0, self._bn - A.shape[0]))
+        # panel-major storage: panel la = columns [la*w, (la+1)*w) of the tile, contiguous (bn x w)
+        self._A_panels = [A[:, la * self._w:(la + 1) * self._w].contiguous() for la in range(self._pa)]
+        self.A = A if self._pa > 1 else self._A_panels[0]
+        self._At_panels = self._exchange_adjoint_panels()
         self.dims = (self.K, self.M)
         self.dimsd = (self.N, self.M)
         shape = (int(np.prod(self.dimsd)), int(np.prod(self.dims)))
-        MPILinearOperator.__init__(self, shape=shape, dtype=_lib.numpy_dtype(_xdtype(self.A.dtype)),
+        MPILinearOperator.__init__(self, shape=shape, dtype=_lib.numpy_dtype(_xdtype(A.dtype)),
                                    base_comm=base_comm)
+        self._side = None
 
-    def _exchange_transposed(self, A: torch.Tensor) -> torch.Tensor:
-        """tile A_{col_id,row_id} (from the transposed grid position), exchanged once"""
-        P = self._P_prime
-        partner = self._col_id * P + self._row_id
-        if partner == self.base_comm.Get_rank() or self.base_comm.Get_size() == 1:
-            return A
-        out = torch.empty_like(A)
+    # ---- grid bookkeeping ------------------------------------------------------------------------
+    def _extent(self, blk: int, full: int, idx: int, nblk: int) -> int:
+        """true (unpadded) extent of block idx out of nblk blocks of padded size blk"""
+        return max(0, min(full, (idx + 1) * blk) - idx * blk)
+
+    def _adj_panel_src(self, i: int, p: int):
+        """adjoint panel p of grid row i is A_{r,l}: returns (r, l, owner rank, owner local panel)"""
+        r = p // self._px
+        l = i * self._px + p % self._px
+        return r, l, r * self._Pc + l // self._pa, l % self._pa
+
+    def _exchange_adjoint_panels(self):
+        """one-off re-distribution for the adjoint: rank (i, jc) keeps panels p with p // pa == jc"""
+        Pr, Pc, L, pa = self._Pr, self._Pc, self._L, self._pa
+        me = self.base_comm.Get_rank()
+        mine = [None] * pa
+        if self.base_comm.Get_size() == 1:
+            return list(self._A_panels)
+        sends, recvs = [], []
+        for i in range(Pr):
+            for p in range(L):
+                r, l, src, la = self._adj_panel_src(i, p)
+                dst = i * Pc + p // pa
+                if src == me and dst == me:
+                    mine[p % pa] = self._A_panels[la]
+                elif src == me:
+                    sends.append((dst, self._A_panels[la]))
+                elif dst == me:
+                    buf = torch.empty_like(self._A_panels[0])
+                    mine[p % pa] = buf
+                    recvs.append((src, buf))
         with group(self.base_comm):
-            send(self.base_comm, A, partner)
-            recv(self.base_comm, out, partner)
-        return out
+            for dst, t in sends:
+                send(self.base_comm, t, dst)
+            for src, t in recvs:
+                recv(self.base_comm, t, src)
+        return mine
 
-    def _local_extent(self, b: int, full: int, idx: int) -> int:
-        return b if idx != self._P_prime - 1 else full - (self._P_prime - 1) * b
+    def _tile_sizes(self, rows_blk: int, rows_full: int):
+        sizes = []
+        for r in range(self.size):
+            ri, ci = divmod(r, self._Pc)
+            sizes.append(self._extent(rows_blk, rows_full, ri, self._Pr) * self._extent(self._bm, self.M, ci, self._Pc))
+        return sizes
 
-    def _padded_block(self, x: DistributedArray, rows_b: int, rows_full: int, xdt) -> Tuple[torch.Tensor, int, int]:
-        P = self._P_prime
-        bm = self._M_padded // P
-        local_r = self._local_extent(rows_b, rows_full, self._row_id)
-        local_m = self._local_extent(bm, self.M, self._col_id)
+    def _padded_block(self, x: DistributedArray, rows_blk: int, rows_full: int, xdt):
+        local_r = self._extent(rows_blk, rows_full, self._row_id, self._Pr)
+        local_m = self._extent(self._bm, self.M, self._col_id, self._Pc)
         blk = x.local_array.to(xdt).reshape(local_r, local_m)
-        if local_r != rows_b or local_m != bm:
-            blk = torch.nn.functional.pad(blk, (0, bm - local_m, 0, rows_b - local_r))
+        if local_r != rows_blk or local_m != self._bm:
+            blk = torch.nn.functional.pad(blk, (0, self._bm - local_m, 0, rows_blk - local_r))
         return blk.contiguous(), local_r, local_m
 
+    def _pipeline(self, nrounds, fetch, compute):
+        """run `compute(l, bufs)` for l < nrounds with `fetch(l)` (the broadcasts of round l, returns
+        bufs) issued one round ahead on a side stream"""
+        if self.base_comm.Get_size() == 1:
+            for l in range(nrounds):
+                compute(l, fetch(l))
+            return
+        main = torch.cuda.current_stream()
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        side = self._side
+        start = torch.cuda.Event()
+        start.record(main)
+        side.wait_event(start)
+        done_compute = [None, None]          # compute events guarding buffer reuse (slot l % 2)
+        pending = None
+        for l in range(nrounds + 1):
+            nxt = None
+            if l < nrounds:
+                with torch.cuda.stream(side):
+                    if done_compute[l % 2] is not None:
+                        side.wait_event(done_compute[l % 2])
+                    bufs = fetch(l)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                nxt = (l, bufs, ev)
+            if pending is not None:
+                pl, pbufs, pev = pending
+                main.wait_event(pev)
+                compute(pl, pbufs)
+                ce = torch.cuda.Event()
+                ce.record(main)
+                done_compute[pl % 2] = ce
+            pending = nxt
+
+    # ---- forward: Y_ij = sum_l A_i,l X_l,j  (MatrixMult.py:612-674) --------------------------------------
     def _matvec(self, x: DistributedArray) -> DistributedArray:
         if x.partition != Partition.SCATTER:
             raise ValueError(f"x should have partition={Partition.SCATTER} Got {x.partition} instead...")
-        P = self._P_prime
-        xdt = _xdtype(self.A.dtype)
-        bn, bk, bm = self._N_padded // P, self._K_padded // P, self._M_padded // P
-        local_n = self._local_extent(bn, self.N, self._row_id)
-        sizes = []
-        for r in range(self.size):
-            ri, ci = divmod(r, P)
-            sizes.append(self._local_extent(bn, self.N, ri) * self._local_extent(bm, self.M, ci))
-        y = DistributedArray(global_shape=(self.N * self.M), mask=x.mask, local_shapes=sizes,
-                             partition=Partition.SCATTER, dtype=xdt, base_comm=x.base_comm)
-        x_block, local_k, local_m = self._padded_block(x, bk, self.K, xdt)
-        Y_local = torch.empty((self.A.shape[0], bm), dtype=xdt, device=x_block.device)
-        Atemp = torch.empty_like(self.A) if P > 1 else None
-        Xtemp = torch.empty_like(x_block) if P > 1 else None
-        for k in range(P):
-            # MatrixMult.py:663-670: Bcast A_k along the row, X_k along the column, accumulate
-            if P == 1:
-                a_k, x_k = self.A, x_block
-            else:
-                a_k = self.A if self._col_id == k else Atemp
-                x_k = x_block if self._row_id == k else Xtemp
-                bcast_(self._row_comm, a_k, root=k)
-                bcast_(self._col_comm, x_k, root=k)
-            tile_product(a_k, x_k, Y_local, _lib.OP_N, accumulate=(k > 0))
+        xdt = _xdtype(self._A_panels[0].dtype)
+        bkX = self._w * self._px
+        y = DistributedArray(global_shape=(self.N * self.M), mask=x.mask,
+                             local_shapes=self._tile_sizes(self._bn, self.N), partition=Partition.SCATTER,
+                             dtype=xdt, base_comm=x.base_comm)
+        x_block, local_k, local_m = self._padded_block(x, bkX, self.K, xdt)
+        local_n = self._extent(self._bn, self.N, self._row_id, self._Pr)
+        Y_local = torch.empty((self._bn, self._bm), dtype=xdt, device=x_block.device)
+        a_tmp = [torch.empty_like(self._A_panels[0]) for _ in range(2)] if self.size > 1 else None
+        x_tmp = [torch.empty((self._w, self._bm), dtype=xdt, device=x_block.device) for _ in range(2)] \
+            if self.size > 1 else None
+        w, pa, px = self._w, self._pa, self._px
+
+        def fetch(l):
+            a_root, la = l // pa, l % pa
+            x_root, lx = l // px, l % px
+            xp = x_block[lx * w:(lx + 1) * w]
+            if self.size == 1:
+                return self._A_panels[la], xp
+            a_k = self._A_panels[la] if self._col_id == a_root else a_tmp[l % 2]
+            x_k = xp if self._row_id == x_root else x_tmp[l % 2]
+            bcast_(self._row_comm, a_k, root=a_root)
+            bcast_(self._col_comm, x_k, root=x_root)
+            return a_k, x_k
+
+        def compute(l, bufs):
+            tile_product(bufs[0], bufs[1], Y_local, _lib.OP_N, accumulate=(l > 0))
+
+        self._pipeline(self._L, fetch, compute)
         y.local_array.copy_(Y_local[:local_n, :local_m].reshape(-1))
         return y
 
+    # ---- adjoint: Xadj_ij = sum_r sum_{l in tile i} (A_r,l)^H Y_r,j  (MatrixMult.py:676-767) -----------------
     def _rmatvec(self, x: DistributedArray) -> DistributedArray:
         if x.partition != Partition.SCATTER:
             raise ValueError(f"x should have partition={Partition.SCATTER}. Got {x.partition} instead.")
-        P = self._P_prime
-        xdt = _xdtype(self.A.dtype)
-        bn, bk, bm = self._N_padded // P, self._K_padded // P, self._M_padded // P
-        local_k = self._local_extent(bk, self.K, self._row_id)
-        sizes = []
-        for r in range(self.size):
-            ri, ci = divmod(r, P)
-            sizes.append(self._local_extent(bk, self.K, ri) * self._local_extent(bm, self.M, ci))
-        y = DistributedArray(global_shape=(self.K * self.M), mask=x.mask, local_shapes=sizes,
-                             partition=Partition.SCATTER, dtype=xdt, base_comm=x.base_comm)
-        x_block, local_n, local_m = self._padded_block(x, bn, self.N, xdt)
-        Y_local = torch.empty((self.A.shape[1], bm), dtype=xdt, device=x_block.device)
-        # result tile (i, j) = sum_k (A_{k,i})^H X_{k,j}  (MatrixMult.py:742-763).  Rank (i, j)
-        # holds A_{j,i} (transposed-grid copy); A_{k,i} lives on rank (i, k) of grid row i ->
-        # a ROW broadcast of the transposed copies, root k.
-        Atemp = torch.empty_like(self._At_src) if P > 1 else None
-        Xtemp = torch.empty_like(x_block) if P > 1 else None
-        for k in range(P):
-            if P == 1:
-                a_k, x_k = self._At_src, x_block
-            else:
-                a_k = self._At_src if self._col_id == k else Atemp
-                x_k = x_block if self._row_id == k else Xtemp
-                bcast_(self._row_comm, a_k, root=k)
-                bcast_(self._col_comm, x_k, root=k)
-            tile_product(a_k, x_k, Y_local, _lib.OP_H, accumulate=(k > 0))
+        xdt = _xdtype(self._A_panels[0].dtype)
+        bkX = self._w * self._px
+        y = DistributedArray(global_shape=(self.K * self.M), mask=x.mask,
+                             local_shapes=self._tile_sizes(bkX, self.K), partition=Partition.SCATTER,
+                             dtype=xdt, base_comm=x.base_comm)
+        x_block, local_n, local_m = self._padded_block(x, self._bn, self.N, xdt)
+        local_k = self._extent(bkX, self.K, self._row_id, self._Pr)
+        Y_local = torch.zeros((bkX, self._bm), dtype=xdt, device=x_block.device)
+        a_tmp = [torch.empty_like(self._A_panels[0]) for _ in range(2)] if self.size > 1 else None
+        x_tmp = [torch.empty_like(x_block) for _ in range(2)] if self.size > 1 else None
+        w, pa, px = self._w, self._pa, self._px
+        state = {"r": -1, "buf": None}
+
+        def fetch(p):
+            a_root = p // pa
+            r = p // px
+            if self.size == 1:
+                return self._At_panels[p % pa], x_block
+            a_k = self._At_panels[p % pa] if self._col_id == a_root else a_tmp[p % 2]
+            bcast_(self._row_comm, a_k, root=a_root)
+            if r != state["r"]:               # Y_r,j is shared by the px panels of round-group r
+                y_k = x_block if self._row_id == r else x_tmp[r % 2]
+                bcast_(self._col_comm, y_k, root=r)
+                state["r"], state["buf"] = r, y_k
+            return a_k, state["buf"]
+
+        def compute(p, bufs):
+            lx = p % px
+            tile_product(bufs[0], bufs[1], Y_local[lx * w:(lx + 1) * w], _lib.OP_H, accumulate=(p // px > 0))
+
+        self._pipeline(self._L, fetch, compute)
         y.local_array.copy_(Y_local[:local_k, :local_m].reshape(-1))
         return y
 
 
 def MPIMatrixMult(A, M: int, saveAt: bool = False, base_comm=COMM_WORLD, kind: str = "summa",
-                  dtype="float64", base_comm_nccl=None):
-    """Factory with the reference's signature (MatrixMult.py:770-874)."""
+                  dtype="float64", base_comm_nccl=None, grid=None):
+    """Factory with the reference's signature (MatrixMult.py:770-874); ``grid=(Pr, Pc)`` is the
+    rectangular-grid extension of the SUMMA variant."""
     if kind == "summa":
-        return _MPISummaMatrixMult(A, M, saveAt, base_comm, dtype, base_comm_nccl)
+        return _MPISummaMatrixMult(A, M, saveAt, base_comm, dtype, base_comm_nccl, grid=grid)
     elif kind == "block":
         return _MPIBlockMatrixMult(A, M, saveAt, base_comm, dtype, base_comm_nccl)
     else:

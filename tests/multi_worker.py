@@ -177,6 +177,30 @@ if Pp * Pp == P:
         xb = Bop.H @ yb
         check("blockH", host(xb.local_array).reshape(K, -1), (A.conj().T @ Yref)[:, ri * bc:min(M, (ri + 1) * bc)], rtol * 10, 0)
 
+# ---- rectangular-grid SUMMA (extension; BASELINE config 4 uses 2 x 4): vs dense products ------------------
+for (Pr, Pc) in [(g, P // g) for g in range(1, P + 1) if P % g == 0]:
+    for (N, K, M, dtype) in [(64, 48, 40, np.float64), (37, 29, 23, np.float64), (24, 36, 16, np.complex128)]:
+        A = comm.bcast(np.random.default_rng(11).standard_normal((N, K)), 0).astype(dtype)
+        X = comm.bcast(np.random.default_rng(12).standard_normal((K, M)), 0).astype(dtype)
+        if dtype is np.complex128:
+            A, X = A + 0.5j * A[::-1], X - 0.25j * X[::-1]
+        L = Pr * Pc // math.gcd(Pr, Pc)
+        bn, bm = math.ceil(N / Pr), math.ceil(M / Pc)
+        Kp = math.ceil(K / L) * L
+        bkA, bkX = Kp // Pc, Kp // Pr
+        ri, ci = divmod(rank, Pc)
+        Aop = pm.MPIMatrixMult(A[ri * bn:(ri + 1) * bn, ci * bkA:(ci + 1) * bkA].copy(), M, kind="summa",
+                               dtype=dtype, grid=(Pr, Pc))
+        xt = [X[(r // Pc) * bkX:(r // Pc + 1) * bkX, (r % Pc) * bm:(r % Pc + 1) * bm] for r in range(P)]
+        xd = pm.DistributedArray(global_shape=K * M, local_shapes=[t.size for t in xt], dtype=dtype)
+        xd[:] = xt[rank].ravel()
+        y = Aop @ xd
+        Yref = A @ X
+        check(f"rect summa {Pr}x{Pc}", host(y.local_array), Yref[ri * bn:(ri + 1) * bn, ci * bm:(ci + 1) * bm].ravel(), 1e-11, 1e-11)
+        xa = Aop.H @ y
+        Xref = A.conj().T @ Yref
+        check(f"rect summaH {Pr}x{Pc}", host(xa.local_array), Xref[ri * bkX:(ri + 1) * bkX, ci * bm:(ci + 1) * bm].ravel(), 1e-10, 1e-10)
+
 # ---- MPIFredholm1 (test_fredholm.py) -------------------------------------------------------------------
 for nz in (5, 1):
     for dtype in (np.float64, np.complex64):
