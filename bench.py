@@ -175,8 +175,10 @@ def time_loop(fn, steps, warmup, comm=None):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t_cpu = time.perf_counter()
     for _ in range(steps):
         fn()
+    time_loop.last_enqueue_ms = (time.perf_counter() - t_cpu) * 1e3 / max(steps, 1)
     e1.record()
     torch.cuda.synchronize()
     if comm is not None:
@@ -221,6 +223,7 @@ def run_gpu_arm(args):
     for _ in range(args.warmup):
         step()
     ms = time_loop(step, args.steps, 0, comm)
+    enqueue_ms = time_loop.last_enqueue_ms     # host time to enqueue one step (GPU-bound if << ms_per_step)
     value = bytes_loc * size * args.steps / (ms * 1e-3) / 1e9
 
     # ---- roofline of the dominant kernel: live CUDA-event timing of the kernel alone --------
@@ -316,7 +319,8 @@ def run_gpu_arm(args):
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(size), "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "extra": extra}
+                "e2e": e2e, "gpu_launches": args.steps * (1 if size == 1 else 3), "clocks": clocks,
+                "host_enqueue_ms_per_step": enqueue_ms, "extra": extra}
         print(json.dumps(line))
 
 
@@ -447,19 +451,20 @@ def run_extras(pm, L, comm, peaks, args):
             for Mg in (4096, 1):
                 if Mg % Pc:
                     Mg = Pc
-                Sop = pm.MPIMatrixMult(At, Mg, kind="summa", dtype="bfloat16", grid=(Pr, Pc))
-                sizes = [(Kg // Pr) * (Mg // Pc)] * size
-                xs = pm.DistributedArray(global_shape=Kg * Mg, local_shapes=sizes, dtype=np.float32)
-                xs.local_array.normal_()
-                ms = time_loop(lambda: Sop.matvec(xs), 5, 2, comm)
-                fl = 2.0 * Ng * Kg * Mg
-                key = f"summa_bf16_32768_M{Mg}_grid{Pr}x{Pc}"
-                out[key] = {"TF/s": fl * 5 / (ms * 1e-3) / 1e12, "ms": ms / 5,
-                            "frac_tensor_total": fl * 5 / (ms * 1e-3) / 1e12 / (size * peaks.get("bf16_tflops", 1590.0)),
-                            "GB/s_A": 2.0 * Ng * Kg * 5 / (ms * 1e-3) / 1e9}
-                ms = time_loop(lambda: Sop.rmatvec(Sop.matvec(xs)), 3, 1, comm)
-                out[key]["fwd+adj_ms"] = ms / 3
-                del Sop, xs
+                for rep in (False, True):
+                    Sop = pm.MPIMatrixMult(At, Mg, kind="summa", dtype="bfloat16", grid=(Pr, Pc), replicate=rep)
+                    sizes = [(Kg // Pr) * (Mg // Pc)] * size
+                    xs = pm.DistributedArray(global_shape=Kg * Mg, local_shapes=sizes, dtype=np.float32)
+                    xs.local_array.normal_()
+                    ms = time_loop(lambda: Sop.matvec(xs), 5, 2, comm)
+                    fl = 2.0 * Ng * Kg * Mg
+                    key = f"{'replicated' if rep else 'summa'}_bf16_32768_M{Mg}_grid{Pr}x{Pc}"
+                    out[key] = {"TF/s": fl * 5 / (ms * 1e-3) / 1e12, "ms": ms / 5,
+                                "frac_tensor_total": fl * 5 / (ms * 1e-3) / 1e12 / (size * peaks.get("bf16_tflops", 1590.0)),
+                                "GB/s_A": 2.0 * Ng * Kg * 5 / (ms * 1e-3) / 1e9}
+                    ms = time_loop(lambda: Sop.rmatvec(Sop.matvec(xs)), 3, 1, comm)
+                    out[key]["fwd+adj_ms"] = ms / 3
+                    del Sop, xs
             del At
     except Exception as exc:
         out["summa_bf16_32768"] = {"error": repr(exc)}

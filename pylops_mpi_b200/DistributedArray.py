@@ -82,7 +82,7 @@ class DistributedArray(DistributedMixIn):
                  mask: Optional[List[Integral]] = None,
                  engine: Optional[str] = "b200",
                  dtype=np.float64,
-                 _buffer: Optional[torch.Tensor] = None):
+                 _buffer: Optional[torch.Tensor] = None, _trusted: bool = False):
         global_shape = _tup(global_shape)
         if len(global_shape) <= axis:
             raise IndexError(f"Axis {axis} out of range for DistributedArray "
@@ -102,7 +102,8 @@ class DistributedArray(DistributedMixIn):
         size, rank = self._base_comm.Get_size(), self._base_comm.Get_rank()
         if local_shapes is not None:
             local_shapes = [_tup(s) for s in local_shapes]
-            self._check_local_shapes(local_shapes)
+            if not _trusted:  # internal constructions pass shapes derived from validated arrays
+                self._check_local_shapes(local_shapes)
             self._local_shapes = local_shapes
         elif partition in _BCAST:
             self._local_shapes = [global_shape] * size
@@ -307,7 +308,7 @@ class DistributedArray(DistributedMixIn):
                                 partition=self._partition, axis=self._axis,
                                 local_shapes=self._local_shapes,
                                 mask=self._mask if mask == "same" else mask,
-                                dtype=self._tdtype if dtype is None else dtype, _buffer=buffer)
+                                dtype=self._tdtype if dtype is None else dtype, _buffer=buffer, _trusted=True)
 
     def _cont(self) -> torch.Tensor:
         a = self._local_array
@@ -527,7 +528,7 @@ class DistributedArray(DistributedMixIn):
         return DistributedArray(global_shape=int(np.prod(self._global_shape)),
                                 base_comm=self._base_comm, local_shapes=local_shapes,
                                 mask=self._mask, partition=self._partition, dtype=self._tdtype,
-                                _buffer=self._cont().reshape(-1).clone())
+                                _buffer=self._cont().reshape(-1).clone(), _trusted=True)
 
     def _ravel_view(self):
         """flattened DistributedArray SHARING this array's buffer (internal: used on
@@ -536,7 +537,7 @@ class DistributedArray(DistributedMixIn):
         return DistributedArray(global_shape=int(np.prod(self._global_shape)),
                                 base_comm=self._base_comm, local_shapes=local_shapes,
                                 mask=self._mask, partition=self._partition, dtype=self._tdtype,
-                                _buffer=self._cont().reshape(-1))
+                                _buffer=self._cont().reshape(-1), _trusted=True)
 
     def empty_like(self):
         return self._like()

@@ -40,6 +40,7 @@ class MPIFirstDerivative(MPILinearOperator):
         self.edge = edge
         self.order = order
         self._register_multiplications(self.kind, self.order)
+        self._plan_cache = {}
 
     def _register_multiplications(self, kind: str, order: int) -> None:
         # FirstDerivative.py:104-127 (same error behaviour)
@@ -78,16 +79,22 @@ class MPIFirstDerivative(MPILinearOperator):
         mult = 2 if tdt.is_complex else 1
         if real_dt not in (torch.float32, torch.float64):
             raise TypeError(f"MPIFirstDerivative supports float32/64 and complex64/128, got {tdt}")
-        rows = [s[0] for s in x.local_shapes]
+        # per-partition bookkeeping is pure integer work: compute once per (partition, direction)
+        key = (tuple(x._local_shapes), x.rank, bool(adjoint))
+        cached = self._plan_cache.get(key)
+        if cached is None:
+            rows = [s[0] for s in x._local_shapes]
+            need_lo, need_hi = C.c_int(), C.c_int()
+            _lib.check(_lib.lib.b2_first_derivative_halo(self._kind_code, self.order, int(adjoint),
+                                                         C.byref(need_lo), C.byref(need_hi)),
+                       "b2_first_derivative_halo")
+            plan = halo_plan(rows, x.rank, need_lo.value, need_hi.value) if x.size > 1 else None
+            cached = self._plan_cache[key] = (rows, offsets(rows)[x.rank], need_lo.value, need_hi.value, plan)
+        rows, row0, nl, nh, plan = cached
         nloc = rows[x.rank]
         ncols = int(np.prod(self.dims[1:])) * mult if len(self.dims) > 1 else mult
-        row0 = offsets(rows)[x.rank]
-        need_lo, need_hi = C.c_int(), C.c_int()
-        _lib.check(_lib.lib.b2_first_derivative_halo(self._kind_code, self.order, int(adjoint),
-                                                     C.byref(need_lo), C.byref(need_hi)),
-                   "b2_first_derivative_halo")
         y = DistributedArray(global_shape=x.global_shape, base_comm=x.base_comm,
-                             local_shapes=x.local_shapes, axis=x.axis, dtype=tdt)
+                             local_shapes=x._local_shapes, axis=x.axis, dtype=tdt, _trusted=True)
         if nloc == 0:
             return y
         xr = torch.view_as_real(xl).reshape(nloc, ncols) if tdt.is_complex else xl.reshape(nloc, ncols)
@@ -110,7 +117,6 @@ class MPIFirstDerivative(MPILinearOperator):
         if x.size == 1:
             launch(0, nloc, None, 0, None, 0)
             return y
-        plan = halo_plan(rows, x.rank, need_lo.value, need_hi.value)
         n_lo, n_hi = plan["recv_lo"], plan["recv_hi"]
         lo = torch.empty((n_lo, ncols), dtype=real_dt, device=xl.device) if n_lo else None
         hi = torch.empty((n_hi, ncols), dtype=real_dt, device=xl.device) if n_hi else None
@@ -126,7 +132,6 @@ class MPIFirstDerivative(MPILinearOperator):
                 if n_hi:
                     recv(x.base_comm, hi, x.rank + 1)
 
-        nl, nh = need_lo.value, need_hi.value
         if nloc < 2 * (nl + nh) + 1:
             # tiny block: exchange, then one launch
             exchange()

@@ -225,7 +225,8 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
     """
 
     def __init__(self, A, M: int, saveAt: bool = False, base_comm=COMM_WORLD, dtype="float64",
-                 base_comm_nccl=None, grid=None) -> None:
+                 base_comm_nccl=None, grid=None, replicate: bool = False) -> None:
+        self._replicate = bool(replicate)
         base_comm = resolve(base_comm)
         rank, size = base_comm.Get_rank(), base_comm.Get_size()
         if grid is None:
@@ -270,6 +271,77 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
         MPILinearOperator.__init__(self, shape=shape, dtype=_lib.numpy_dtype(_xdtype(A.dtype)),
                                    base_comm=base_comm)
         self._side = None
+        if self._replicate:
+            self._build_replicas()
+
+    # ---- replicated-panel mode (B200-first: spend HBM, not NVLink) --------------------------------
+    def _build_replicas(self):
+        """A is operator STATE, X changes every apply -- yet SUMMA re-broadcasts the A panels on every
+        apply (`:663-670`), which makes a 32768^2 bf16 product on 8 GPUs NVLink-bound.  With 180 GB of
+        HBM per GPU each rank can keep, once, (i) its whole grid-row panel A[i-rows, :] (forward) and
+        (ii) its X-tile's column panel A[:, k-range(i)] (adjoint).  An apply is then ONE allgather of
+        the small operand along the grid column + ONE local tile product at full tensor-core rate.
+        Same sums as SUMMA (different association) -> same result within rounding."""
+        Pr, Pc = self._Pr, self._Pc
+        bn, w = self._bn, self._w
+        Kp, bkX = self._K_padded, self._w * self._px
+        tile = torch.cat(self._A_panels, dim=1) if self._pa > 1 else self._A_panels[0]   # (bn, bkA)
+        if Pc > 1:
+            flat = allgatherv(self._row_comm, tile.reshape(-1), [tile.numel()] * Pc)
+            self._A_row = torch.cat([flat[c * tile.numel():(c + 1) * tile.numel()].view(bn, -1) for c in range(Pc)],
+                                    dim=1).contiguous()                                   # (bn, Kp)
+        else:
+            self._A_row = tile
+        # column panel for the adjoint: rows of all Pr grid rows, columns k-range(row_id)
+        if Pr > 1:
+            blocks, outgoing = [None] * Pr, []
+            with group(self._col_comm):
+                for r in range(Pr):
+                    blk = self._A_row[:, r * bkX:(r + 1) * bkX].contiguous()
+                    if r == self._row_id:
+                        blocks[r] = blk
+                    else:
+                        outgoing.append(blk)
+                        send(self._col_comm, blk, r)
+                        blocks[r] = torch.empty((bn, bkX), dtype=tile.dtype, device=tile.device)
+                        recv(self._col_comm, blocks[r], r)
+            torch.cuda.synchronize()      # construction time: send buffers may now be released
+            del outgoing
+            # blocks[r] (received from grid row r) == A[r-rows, k-range(me)]
+            self._A_col = torch.cat(blocks, dim=0).contiguous()
+        else:
+            self._A_col = self._A_row[:, :bkX].contiguous() if bkX != Kp else self._A_row
+
+    def _gather_col(self, blk: torch.Tensor) -> torch.Tensor:
+        """stack the (rows x bm) tiles of this grid column: (Pr*rows x bm)"""
+        if self._Pr == 1:
+            return blk
+        flat = allgatherv(self._col_comm, blk.reshape(-1), [blk.numel()] * self._Pr)
+        return flat.view(self._Pr * blk.shape[0], blk.shape[1])
+
+    def _apply_replicated(self, x: DistributedArray, adjoint: bool) -> DistributedArray:
+        xdt = _xdtype(self._A_row.dtype)
+        bkX = self._w * self._px
+        rows_in, full_in = (self._bn, self.N) if adjoint else (bkX, self.K)
+        rows_out, full_out = (bkX, self.K) if adjoint else (self._bn, self.N)
+        y = DistributedArray(global_shape=(full_out * self.M), mask=x.mask,
+                             local_shapes=self._tile_sizes(rows_out, full_out), partition=Partition.SCATTER,
+                             dtype=xdt, base_comm=x.base_comm)
+        x_block, _, local_m = self._padded_block(x, rows_in, full_in, xdt)
+        if self._A_row.dtype is torch.bfloat16 and self._bm > 1:
+            x_block = x_block.to(torch.bfloat16)          # halves the allgather payload
+        Xcol = self._gather_col(x_block)
+        local_out = self._extent(rows_out, full_out, self._row_id, self._Pr)
+        direct = (local_out == rows_out and local_m == self._bm)
+        Y_local = y.local_array.view(rows_out, self._bm) if direct else \
+            torch.empty((rows_out, self._bm), dtype=xdt, device=x_block.device)
+        if adjoint:
+            tile_product(self._A_col, Xcol, Y_local, _lib.OP_H, False)
+        else:
+            tile_product(self._A_row, Xcol, Y_local, _lib.OP_N, False)
+        if not direct:
+            y.local_array.copy_(Y_local[:local_out, :local_m].reshape(-1))
+        return y
 
     # ---- grid bookkeeping ------------------------------------------------------------------------
     def _extent(self, blk: int, full: int, idx: int, nblk: int) -> int:
@@ -363,6 +435,8 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
     def _matvec(self, x: DistributedArray) -> DistributedArray:
         if x.partition != Partition.SCATTER:
             raise ValueError(f"x should have partition={Partition.SCATTER} Got {x.partition} instead...")
+        if self._replicate:
+            return self._apply_replicated(x, False)
         xdt = _xdtype(self._A_panels[0].dtype)
         bkX = self._w * self._px
         y = DistributedArray(global_shape=(self.N * self.M), mask=x.mask,
@@ -399,6 +473,8 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
     def _rmatvec(self, x: DistributedArray) -> DistributedArray:
         if x.partition != Partition.SCATTER:
             raise ValueError(f"x should have partition={Partition.SCATTER}. Got {x.partition} instead.")
+        if self._replicate:
+            return self._apply_replicated(x, True)
         xdt = _xdtype(self._A_panels[0].dtype)
         bkX = self._w * self._px
         y = DistributedArray(global_shape=(self.K * self.M), mask=x.mask,
@@ -435,11 +511,12 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
 
 
 def MPIMatrixMult(A, M: int, saveAt: bool = False, base_comm=COMM_WORLD, kind: str = "summa",
-                  dtype="float64", base_comm_nccl=None, grid=None):
+                  dtype="float64", base_comm_nccl=None, grid=None, replicate: bool = False):
     """Factory with the reference's signature (MatrixMult.py:770-874); ``grid=(Pr, Pc)`` is the
-    rectangular-grid extension of the SUMMA variant."""
+    rectangular-grid extension of the SUMMA variant, ``replicate=True`` its replicated-panel mode
+    (A row / column panels kept per rank, one small allgather + one local product per apply)."""
     if kind == "summa":
-        return _MPISummaMatrixMult(A, M, saveAt, base_comm, dtype, base_comm_nccl, grid=grid)
+        return _MPISummaMatrixMult(A, M, saveAt, base_comm, dtype, base_comm_nccl, grid=grid, replicate=replicate)
     elif kind == "block":
         return _MPIBlockMatrixMult(A, M, saveAt, base_comm, dtype, base_comm_nccl)
     else:

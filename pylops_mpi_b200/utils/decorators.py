@@ -36,7 +36,8 @@ def reshaped(func: Optional[Callable] = None, forward: Optional[bool] = None,
             dst = [int(np.prod(s)) for s in local_shapes]
             buf = x._repartition_flat(dst).view(local_shapes[x.rank])
             arr = DistributedArray(global_shape=global_shape, base_comm=x.base_comm,
-                                   local_shapes=local_shapes, axis=0, dtype=x._tdtype, _buffer=buf)
+                                   local_shapes=local_shapes, axis=0, dtype=x._tdtype, _buffer=buf,
+                                   _trusted=(local_shapes is not None))
             y: DistributedArray = f(self, arr)
             if len(y.global_shape) > 1:
                 y = y._ravel_view()      # y is a fresh temporary: flatten without the copy of :74-75

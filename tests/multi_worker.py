@@ -200,6 +200,11 @@ for (Pr, Pc) in [(g, P // g) for g in range(1, P + 1) if P % g == 0]:
         xa = Aop.H @ y
         Xref = A.conj().T @ Yref
         check(f"rect summaH {Pr}x{Pc}", host(xa.local_array), Xref[ri * bkX:(ri + 1) * bkX, ci * bm:(ci + 1) * bm].ravel(), 1e-10, 1e-10)
+        Rop = pm.MPIMatrixMult(A[ri * bn:(ri + 1) * bn, ci * bkA:(ci + 1) * bkA].copy(), M, kind="summa",
+                               dtype=dtype, grid=(Pr, Pc), replicate=True)
+        yr = Rop @ xd
+        check(f"replicated {Pr}x{Pc}", host(yr.local_array), host(y.local_array), 1e-11, 1e-11)
+        check(f"replicatedH {Pr}x{Pc}", host((Rop.H @ yr).local_array), host(xa.local_array), 1e-10, 1e-10)
 
 # ---- MPIFredholm1 (test_fredholm.py) -------------------------------------------------------------------
 for nz in (5, 1):

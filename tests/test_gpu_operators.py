@@ -219,6 +219,10 @@ def test_matrixmult_kats(pm, N, K, M, dtype, kind):
     np.testing.assert_allclose(host(xadj.asarray()).reshape(K, M), A.conj().T @ Yref, rtol=rtol * 10)
     with pytest.raises(ValueError):
         Aop @ pm.DistributedArray.to_dist(X.ravel(), partition=pm.Partition.BROADCAST)
+    if kind == "summa":
+        Rop = pm.MPIMatrixMult(A, M, kind=kind, dtype=dtype, replicate=True)
+        np.testing.assert_allclose(host((Rop @ x).asarray()).reshape(N, M), Yref, rtol=rtol)
+        np.testing.assert_allclose(host((Rop.H @ y).asarray()).reshape(K, M), A.conj().T @ Yref, rtol=rtol * 10)
 
 
 # ---- MPIFredholm1 KATs (test_fredholm.py:36-95, 114-167) ---------------------------------------
