@@ -84,6 +84,11 @@ int b2_norm_partial(b2_ctx* ctx, const void* x, size_t n, int dtype, int kind, d
 int b2_dot_multi(b2_ctx* ctx, int k, const void* const* xs, const void* const* ys, size_t n,
                  int dtype, int conj_x, double* out_dev, void* stream);
 
+/* out = |num / (den1 + alpha * den2)| on DEVICE scalars (den2 may be NULL): the CGLS step length
+ * a = kold / (q.q + damp c.c) and ratio b = k / kold (cls_basic.py:389, 395) with no host sync */
+int b2_scalar_div(double* out_dev, const double* num_dev, const double* den1_dev,
+                  const double* den2_dev, double alpha, void* stream);
+
 /* ---- MPIFirstDerivative per-rank apply (FirstDerivative.py:129-319) -------
  * x,y: this rank's row block [nrows_local x ncols] (C order) of the global
  * [nrows_global x ncols] array, global row offset row0.  halo_lo holds the n_lo

@@ -75,6 +75,7 @@ def _load():
         "b2_dot": ([vp, vp, vp, sz, i, i, vp, vp], i),
         "b2_norm_partial": ([vp, vp, sz, i, i, d, vp, vp], i),
         "b2_dot_multi": ([vp, i, C.POINTER(vp), C.POINTER(vp), sz, i, i, vp, vp], i),
+        "b2_scalar_div": ([vp, vp, vp, vp, d, vp], i),
         "b2_first_derivative": ([vp, vp, vp, vp, i, vp, i, sz, sz, sz, sz, i, i, i, d, i, i, vp], i),
         "b2_first_derivative_halo": ([i, i, i, C.POINTER(i), C.POINTER(i)], i),
         "b2_first_derivative_host": ([vp, vp, vp, sz, sz, sz, sz, i, i, i, d, i, i], i),

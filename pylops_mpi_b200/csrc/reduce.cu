@@ -420,3 +420,25 @@ extern "C" int b2_dot_multi(b2_ctx* ctx, int k, const void* const* xs, const voi
   return conj_x ? launch_multi<double, true, true>(ctx, k, p, 2 * n, out_dev, st)
                 : launch_multi<double, true, false>(ctx, k, p, 2 * n, out_dev, st);
 }
+
+// ---- device-resident scalar arithmetic for solver recurrences ------------------------
+// out = num / (den1 + alpha * den2)   (den2 may be NULL): CGLS step length
+// a = kold / (q.q + damp * c.c) and ratio b = k / kold (cls_basic.py:389, 395) without a host round trip
+namespace {
+__global__ void scalar_div_kernel(double* out, const double* num, const double* den1, const double* den2,
+                                  double alpha) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double d = *den1;
+    if (den2) d += alpha * (*den2);
+    *out = fabs(*num / d);
+  }
+}
+}  // namespace
+
+extern "C" int b2_scalar_div(double* out_dev, const double* num_dev, const double* den1_dev,
+                             const double* den2_dev, double alpha, void* stream) {
+  if (!out_dev || !num_dev || !den1_dev) return B2_ERR_ARG;
+  scalar_div_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(out_dev, num_dev, den1_dev, den2_dev, alpha);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}

@@ -72,6 +72,52 @@ def _self_dots(arrs: Sequence[DistributedArray]) -> List[float]:
     return [float(np.abs(res[i])) for i in range(k)]
 
 
+def _dots_device(arrs: Sequence[DistributedArray], out: torch.Tensor, offset: int = 0) -> int:
+    """out[offset + i*stride] = a_i . conj(a_i) (LOCAL partial sums, float64, no host sync);
+    returns the number of doubles written.  One launch when all arrays share a length."""
+    import ctypes as C
+    views = [a._scatter_view() for a in arrs]
+    stride = 2 if views[0].dtype.is_complex else 1
+    n0 = views[0].numel()
+    if all(v.numel() == n0 for v in views) and len(views) <= 4:
+        groups = [views]
+    else:
+        groups = [[v] for v in views]
+    off = offset
+    for g in groups:
+        k = len(g)
+        n = g[0].numel()
+        ptrs = (C.c_void_p * k)(*[v.data_ptr() if n else None for v in g])
+        _lib.check(_lib.lib.b2_dot_multi(_lib.ctx(), k, ptrs, ptrs, n, _lib.code(g[0].dtype), 1,
+                                         out.data_ptr() + 8 * off, _lib.stream()), "b2_dot_multi")
+        off += k * stride
+    return off - offset
+
+
+def _scalar_div(out: torch.Tensor, oi: int, num: torch.Tensor, ni: int, den1: torch.Tensor, d1: int,
+                den2: Optional[torch.Tensor] = None, d2: int = 0, alpha: float = 0.0):
+    """out[oi] = |num[ni] / (den1[d1] + alpha * den2[d2])| on the device"""
+    _lib.check(_lib.lib.b2_scalar_div(out.data_ptr() + 8 * oi, num.data_ptr() + 8 * ni, den1.data_ptr() + 8 * d1,
+                                      (den2.data_ptr() + 8 * d2) if den2 is not None else None, float(alpha),
+                                      _lib.stream()), "b2_scalar_div")
+
+
+def _lincomb_dev(out: DistributedArray, a_dev: Optional[torch.Tensor], ai: int, a_scale: float,
+                 x: DistributedArray, b_dev: Optional[torch.Tensor], bi: int, b_scale: float,
+                 y: DistributedArray):
+    """out = (a_scale * a_dev[ai]) * x + (b_scale * b_dev[bi]) * y with DEVICE scalars (NULL -> 1)"""
+    o, xv, yv = out._cont(), x._cont(), y._cont()
+    n = o.numel()
+    if n:
+        _lib.check(_lib.lib.b2_lincomb_dev(_lib.ctx(), o.data_ptr(),
+                                           (a_dev.data_ptr() + 8 * ai) if a_dev is not None else None, float(a_scale),
+                                           xv.data_ptr(),
+                                           (b_dev.data_ptr() + 8 * bi) if b_dev is not None else None, float(b_scale),
+                                           yv.data_ptr(), n, _lib.code(o.dtype), _lib.stream()), "b2_lincomb_dev")
+    if o is not out.local_array:
+        out.local_array.copy_(o)
+
+
 class CG(Solver):
     """cls_basic.py:12-249"""
 
@@ -148,6 +194,10 @@ class CGLS(Solver):
         self.c = r.copy()
         self.q = self.Op.matvec(self.c)
         self.kold = _self_dots([r])[0]
+        # device-resident scalars for the fused step: [qq, cc | k, ss, xx | a, b | kold] (x2 if complex)
+        self._st = 2 if x._tdtype.is_complex else 1
+        self._dev = torch.zeros(16, dtype=torch.float64, device=x.local_array.device)
+        self._dev[14] = self.kold
         self.cost = []
         self.cost1 = []
         ss, xx = _self_dots([self.s, x]) if self.s.local_shape == x.local_shape else \
@@ -164,26 +214,33 @@ class CGLS(Solver):
         return x
 
     def step(self, x, show: bool = False):
-        if self.q.local_shape == self.c.local_shape:
-            qq, cc = _self_dots([self.q, self.c])
-        else:
-            qq, cc = _self_dots([self.q])[0], _self_dots([self.c])[0]
-        a = float(np.abs(self.kold / (qq + self.damp * cc)))
-        x.axpy_(a, self.c)                          # x += a * c          (:390)
-        self.s.axpy_(-a, self.q)                    # s -= a * q          (:391)
-        r = self.Op.rmatvec(self.s)                 # r = Op^H s - damp x (:392-393)
+        """One CGLS iteration (cls_basic.py:370-404) with the scalars a, b kept on the device:
+        2 Allreduces and ONE host synchronisation per iteration (the reference: 5 and 5)."""
+        dev, st = self._dev, self._st
+        QQ, CC, K, SS, XX, A_, B_, KOLD = 0, st, 4, 4 + st, 4 + 2 * st, 12, 13, 14
+        sub = self.c.sub_comm
+        # a = |kold / (q.q + damp c.c)|                                                  (:389)
+        _dots_device([self.q], dev, QQ)
+        _dots_device([self.c], dev, CC)
+        allreduce_(sub, dev[0:2 * st], "sum")
+        _scalar_div(dev, A_, dev, KOLD, dev, QQ, dev, CC, self.damp)
+        _lincomb_dev(x, dev, A_, 1.0, self.c, None, 0, 1.0, x)            # x += a c       (:390)
+        _lincomb_dev(self.s, dev, A_, -1.0, self.q, None, 0, 1.0, self.s)  # s -= a q       (:391)
+        r = self.Op.rmatvec(self.s)                                        # r = Op^H s - damp x
         if self.damp != 0.0:
             r.axpy_(-self.damp, x)
-        k = _self_dots([r])[0]
-        b = float(k / self.kold)
-        self.c.xpby_(r, b)                          # c = r + b * c       (:396)
+        _dots_device([r], dev, K)
+        _dots_device([self.s], dev, SS)
+        _dots_device([x], dev, XX)
+        allreduce_(sub, dev[4:4 + 3 * st], "sum")
+        _scalar_div(dev, B_, dev, K, dev, KOLD)                            # b = k / kold   (:395)
+        _lincomb_dev(self.c, None, 0, 1.0, r, dev, B_, 1.0, self.c)        # c = r + b c    (:396)
         self.q = self.Op.matvec(self.c)
+        host = dev[4:4 + 3 * st].cpu().numpy()                             # the one sync of the iteration
+        dev[KOLD:KOLD + 1].copy_(dev[K:K + 1])
+        k, ss, xx = (float(abs(host[i * st])) for i in range(3))
         self.kold = k
         self.iiter += 1
-        if self.s.local_shape == x.local_shape:
-            ss, xx = _self_dots([self.s, x])
-        else:
-            ss, xx = _self_dots([self.s])[0], _self_dots([x])[0]
         self.cost.append(float(np.sqrt(ss)))
         self.cost1.append(np.sqrt(float(self.cost[self.iiter] ** 2 + self.damp * xx)))
         if show and self.rank == 0:

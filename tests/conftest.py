@@ -11,6 +11,17 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # make sure libb200lops.so exists / is current before any test imports the package
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_b200_build", os.path.join(ROOT, "pylops_mpi_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    try:
+        mod.build()
+    except Exception as exc:  # e.g. no nvcc on the box: the prebuilt in-tree .so is used
+        if not os.path.exists(mod.OUT):
+            raise
+        print(f"[conftest] using prebuilt {mod.OUT} ({exc})")
 
 
 def pytest_collection_modifyitems(config, items):

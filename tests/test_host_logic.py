@@ -16,7 +16,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_abi_library_loads_and_exports_every_declared_symbol():
-    from pylops_mpi_b200 import build
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_b200_build", os.path.join(ROOT, "pylops_mpi_b200", "build.py"))
+    build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(build)  # not via the package: importing it needs the built library
     path = build.build()            # builds on first use (nvcc cross-compiles without a GPU)
     lib = ctypes.CDLL(path)
     header = open(os.path.join(ROOT, "include", "b200lops.h")).read()
