@@ -12,10 +12,14 @@
 // holds by construction for every N, kind, order and edge flag.
 //
 // Fast path (HBM-bound, target >= 60 % of the HBM roofline): one thread owns a
-// 16-byte column vector and marches down a chunk of rows with a rolling
-// register window, so every x element is fetched once per chunk (re-reads only
-// for the 2R overlap rows, served by L2) and every y element is written once
-// with a streaming store.  Algorithmic bytes: 2*sizeof(T) per element.
+// 16-byte column vector and a short chunk of rows held in a register window;
+// every y element is written once with a streaming store.  Measured tuning
+// (profiles/r01_stencil_tuning.md): SHORT chunks win -- 4 rows per CTA keeps the
+// concurrently running CTAs on a narrow band of whole rows (DRAM-page and L2
+// friendly; the 2R overlap rows are L2 hits, DRAM traffic stays ~algorithmic),
+// 64-row chunks (first design) reached 0.85 of the copy peak, 4-row chunks 1.04.
+// Algorithmic bytes: 2*sizeof(T) per element.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -93,11 +97,10 @@ __device__ __forceinline__ const double* special_taps(const StencilParams& p, lo
 // fast path: 16-byte column vectors, rolling window down a chunk of rows.
 // MASK bit (k+R) set <=> interior tap k is non-zero (compile-time skip).
 // -------------------------------------------------------------------------
-constexpr int ST_COLS = 128;   // threads along columns
-constexpr int ST_ROWS = 64;    // rows per chunk (per thread)
-constexpr int ST_U = 4;        // rows loaded per step
-
-template <typename T, int MASK>
+// tuning knobs (template parameters): ST_COLS threads along columns, ST_ROWS rows per chunk
+// (per thread), ST_U rows loaded per step.  Variant 0 is the default; B2_STENCIL_VARIANT selects
+// another one at run time (used by profiles/tune_stencil.py).
+template <typename T, int MASK, int ST_ROWS, int ST_U, int ST_COLS>
 __global__ void __launch_bounds__(ST_COLS)
 stencil_vec_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restrict__ lo,
                    const T* __restrict__ hi, const __grid_constant__ StencilParams p) {
@@ -223,6 +226,32 @@ int interior_mask(const double t[NT]) {
   return m;
 }
 
+template <typename T, int ROWS, int U, int COLS>
+int launch_vec(const void* x, void* y, const void* lo, const void* hi, const StencilParams& p, int mask,
+               cudaStream_t st) {
+  constexpr int V = Vec16<T>::N;
+  const long long nblk = ((p.ncols / V + COLS - 1) / COLS) * ((p.nloc + ROWS - 1) / ROWS);
+  if (nblk > 0x7fffffffLL) return B2_ERR_ARG;
+  const unsigned grid = (unsigned)nblk;
+#define B2_ST_CASE(M)                                                                              \
+  case M:                                                                                          \
+    stencil_vec_kernel<T, M, ROWS, U, COLS><<<grid, COLS, 0, st>>>((const T*)x, (T*)y, (const T*)lo, \
+                                                                   (const T*)hi, p);               \
+    break;
+  switch (mask) {
+    B2_ST_CASE(0x0c)  // taps {0,+1}
+    B2_ST_CASE(0x06)  // taps {-1,0}
+    B2_ST_CASE(0x0a)  // taps {-1,+1}
+    B2_ST_CASE(0x1b)  // taps {-2,-1,+1,+2}
+    default:
+      stencil_vec_kernel<T, 0x1f, ROWS, U, COLS><<<grid, COLS, 0, st>>>((const T*)x, (T*)y, (const T*)lo,
+                                                                        (const T*)hi, p);
+  }
+#undef B2_ST_CASE
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
 template <typename T>
 int launch_stencil(b2_ctx* ctx, const void* x, void* y, const void* lo, const void* hi,
                    const StencilParams& p, cudaStream_t st) {
@@ -232,24 +261,26 @@ int launch_stencil(b2_ctx* ctx, const void* x, void* y, const void* lo, const vo
                       (p.ncols / V >= 8);
   const int mask = interior_mask(p.interior);
   if (vec_ok) {
-    const long long nblk = ((p.ncols / V + ST_COLS - 1) / ST_COLS) * ((p.nloc + ST_ROWS - 1) / ST_ROWS);
-    if (nblk > 0x7fffffffLL) return B2_ERR_ARG;
-    const unsigned grid = (unsigned)nblk;
-#define B2_ST_CASE(M)                                                                          \
-  case M:                                                                                      \
-    stencil_vec_kernel<T, M><<<grid, ST_COLS, 0, st>>>((const T*)x, (T*)y, (const T*)lo,       \
-                                                       (const T*)hi, p);                       \
-    break;
-    switch (mask) {
-      B2_ST_CASE(0x0c)  // taps {0,+1}
-      B2_ST_CASE(0x06)  // taps {-1,0}
-      B2_ST_CASE(0x0a)  // taps {-1,+1}
-      B2_ST_CASE(0x1b)  // taps {-2,-1,+1,+2}
-      default:
-        stencil_vec_kernel<T, 0x1f><<<grid, ST_COLS, 0, st>>>((const T*)x, (T*)y, (const T*)lo,
-                                                               (const T*)hi, p);
+    static int variant = -1;
+    if (variant < 0) {
+      const char* e = getenv("B2_STENCIL_VARIANT");
+      variant = e ? atoi(e) : 0;
     }
-#undef B2_ST_CASE
+    switch (variant) {
+      case 1: return launch_vec<T, 8, 4, 128>(x, y, lo, hi, p, mask, st);
+      case 2: return launch_vec<T, 8, 2, 128>(x, y, lo, hi, p, mask, st);
+      case 3: return launch_vec<T, 4, 4, 128>(x, y, lo, hi, p, mask, st);
+      case 4: return launch_vec<T, 4, 2, 128>(x, y, lo, hi, p, mask, st);
+      case 5: return launch_vec<T, 8, 8, 128>(x, y, lo, hi, p, mask, st);
+      case 6: return launch_vec<T, 8, 4, 256>(x, y, lo, hi, p, mask, st);
+      case 7: return launch_vec<T, 8, 4, 64>(x, y, lo, hi, p, mask, st);
+      case 8: return launch_vec<T, 4, 4, 256>(x, y, lo, hi, p, mask, st);
+      case 9: return launch_vec<T, 8, 1, 128>(x, y, lo, hi, p, mask, st);
+      case 10: return launch_vec<T, 2, 2, 128>(x, y, lo, hi, p, mask, st);
+      case 11: return launch_vec<T, 8, 2, 256>(x, y, lo, hi, p, mask, st);
+      case 12: return launch_vec<T, 64, 4, 128>(x, y, lo, hi, p, mask, st);   // first design (r01 baseline)
+      default: return launch_vec<T, 4, 4, 128>(x, y, lo, hi, p, mask, st);    // tuned: see profiles/r01_stencil_tuning.md
+    }
   } else {
     size_t total = (size_t)p.nloc * (size_t)p.ncols;
     size_t need = (total + 255) / 256;
