@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("nproc", [2, 4])
+@pytest.mark.parametrize("nproc", [2, 4, 8])
 def test_multi_rank_parity(nproc):
     if torch.cuda.device_count() < nproc:
         pytest.skip(f"needs {nproc} GPUs, box has {torch.cuda.device_count()}")
