@@ -18,6 +18,7 @@
 // Row-major operands map onto UMMA "major" modes without any transposition copy:
 //   A op=N  -> K-major,   A op=T -> MN-major,   B (k x n row-major) -> MN-major.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -352,6 +353,9 @@ __global__ void zero_c_kernel(float* C, size_t ldc, size_t m, size_t n) {
 
 }  // namespace
 
+int b2_gemm_bf16_2cta(b2_ctx* ctx, const void* A, size_t lda, const void* B, size_t ldb, float* C, size_t ldc,
+                      size_t m, size_t n, size_t k, int op_a, int accumulate, cudaStream_t st);
+
 extern "C" int b2_gemm_bf16(b2_ctx* ctx, const void* A, size_t lda, const void* B, size_t ldb, float* C,
                             size_t ldc, size_t m, size_t n, size_t k, int op_a, int accumulate,
                             void* stream) {
@@ -371,6 +375,15 @@ extern "C" int b2_gemm_bf16(b2_ctx* ctx, const void* A, size_t lda, const void* 
   if (m > 0x7fffffffu || n > 0x7fffffffu || k > 0x7fffffffu) return B2_ERR_ARG;
   // TMA: 16-byte aligned bases, row pitches multiple of 16 bytes
   if (!b2_aligned16(A) || !b2_aligned16(B) || (lda % 8) || (ldb % 8)) return B2_ERR_ALIGN;
+  {
+    // kernel selection: B2_GEMM_2CTA=1 -> cta_group::2 pair kernel (gemm_tc2.cu), 0 -> 1-CTA kernel
+    static int use2 = -1;
+    if (use2 < 0) {
+      const char* e = getenv("B2_GEMM_2CTA");
+      use2 = e ? atoi(e) : 0;
+    }
+    if (use2 && m > BM) return b2_gemm_bf16_2cta(ctx, A, lda, B, ldb, C, ldc, m, n, k, op_a, accumulate, st);
+  }
   const bool a_mn = (op_a != B2_OP_N);
   CUtensorMap tmA, tmB;
   int rc;

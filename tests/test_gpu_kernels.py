@@ -362,3 +362,14 @@ def test_gemm_bf16_alignment_error_is_loud(L):
     Cm = torch.zeros(8, 8, device="cuda")
     rc = L.lib.b2_gemm_bf16(L.ctx(), A.data_ptr(), 12, B.data_ptr(), 8, Cm.data_ptr(), 8, 8, 8, 12, 0, 0, L.stream())
     assert rc == 2006
+
+
+def test_gemm_bf16_2cta_variant():
+    """cta_group::2 kernel (selected by B2_GEMM_2CTA=1, latched at first use -> own process)"""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "gemm2cta_worker.py")], capture_output=True, text=True,
+                       timeout=240, env=dict(os.environ, B2_GEMM_2CTA="1"))
+    assert r.returncode == 0 and "GEMM2CTA_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
