@@ -136,6 +136,20 @@ int b2_gemm(b2_ctx* ctx, const void* A, size_t lda, const void* B, size_t ldb, v
 int b2_batched_gemm(b2_ctx* ctx, const void* G, const void* x, void* y, size_t nsl, size_t nx,
                     size_t ny, size_t nz, int adjoint, int dtype, void* stream);
 
+/* Fused product + all-gather over NVLink peer memory: the epilogue stores every output element to
+ * y (local) and to the same offset of `npeers` peer buffers (IPC-mapped; peers_host[d] already points
+ * at the position matching y).  Replaces product-then-Allgather of Fredholm1.py:122-132 by ONE kernel;
+ * completion across ranks = any stream-ordered collective after it (e.g. a 1-element b2_allreduce). */
+int b2_batched_gemm_allgather(b2_ctx* ctx, const void* G, const void* x, void* y, void* const* peers_host,
+                              int npeers, size_t nsl, size_t nx, size_t ny, size_t nz, int adjoint,
+                              int dtype, void* stream);
+/* peer-mappable device buffers (cudaMalloc) and CUDA IPC handle plumbing (64-byte handles) */
+int b2_symm_alloc(size_t bytes, void** out);
+int b2_symm_free(void* p);
+int b2_ipc_get_handle(void* p, void* handle64_host);
+int b2_ipc_open_handle(const void* handle64_host, void** out);
+int b2_ipc_close_handle(void* p);
+
 /* ---- NCCL collectives (utils/_nccl.py:98-403, utils/_mpi.py:21-344,
  *      Distributed.py:35-349) --------------------------------------------- */
 int b2_get_unique_id(void* id128_host);                       /* _nccl.py:98-132 */
@@ -151,6 +165,10 @@ int b2_allgather(b2_comm* comm, const void* send, void* recv, size_t n_per_rank,
  * contributes counts[r] elements; recv is the plain concatenation */
 int b2_allgatherv(b2_comm* comm, const void* send, void* recv, const size_t* counts_host,
                   int dtype, void* stream);
+/* same, with explicit placement: rank r's counts[r] elements land at recv + offsets[r] (elements);
+ * send may alias its own destination (in-place).  Enables chunked gather overlapped with compute. */
+int b2_allgatherv_at(b2_comm* comm, const void* send, void* recv, const size_t* counts_host,
+                     const size_t* offsets_host, int dtype, void* stream);
 int b2_bcast(b2_comm* comm, void* buf, size_t n, int dtype, int root, void* stream);  /* :243-262 */
 int b2_send(b2_comm* comm, const void* buf, size_t n, int dtype, int peer, void* stream); /* :265-286 */
 int b2_recv(b2_comm* comm, void* buf, size_t n, int dtype, int peer, void* stream);       /* :289-316 */

@@ -83,6 +83,12 @@ def _load():
         "b2_gemm_bf16": ([vp, vp, sz, vp, sz, vp, sz, sz, sz, sz, i, i, vp], i),
         "b2_gemm": ([vp, vp, sz, vp, sz, vp, sz, sz, sz, sz, i, i, i, vp], i),
         "b2_batched_gemm": ([vp, vp, vp, vp, sz, sz, sz, sz, i, i, vp], i),
+        "b2_batched_gemm_allgather": ([vp, vp, vp, vp, C.POINTER(vp), i, sz, sz, sz, sz, i, i, vp], i),
+        "b2_symm_alloc": ([sz, C.POINTER(vp)], i),
+        "b2_symm_free": ([vp], i),
+        "b2_ipc_get_handle": ([vp, vp], i),
+        "b2_ipc_open_handle": ([vp, C.POINTER(vp)], i),
+        "b2_ipc_close_handle": ([vp], i),
         "b2_get_unique_id": ([vp], i),
         "b2_comm_create": ([i, i, vp, i, C.POINTER(vp)], i),
         "b2_comm_split": ([vp, i, i, C.POINTER(vp)], i),
@@ -91,6 +97,7 @@ def _load():
         "b2_allreduce": ([vp, vp, vp, sz, i, i, vp], i),
         "b2_allgather": ([vp, vp, vp, sz, i, vp], i),
         "b2_allgatherv": ([vp, vp, vp, C.POINTER(sz), i, vp], i),
+        "b2_allgatherv_at": ([vp, vp, vp, C.POINTER(sz), C.POINTER(sz), i, vp], i),
         "b2_bcast": ([vp, vp, sz, i, i, vp], i),
         "b2_send": ([vp, vp, sz, i, i, vp], i),
         "b2_recv": ([vp, vp, sz, i, i, vp], i),

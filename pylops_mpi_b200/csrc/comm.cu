@@ -168,3 +168,26 @@ extern "C" int b2_recv(b2_comm* comm, void* buf, size_t n, int dtype, int peer, 
 
 extern "C" int b2_group_start(void) { B2_NCCL(ncclGroupStart()); return B2_OK; }
 extern "C" int b2_group_end(void) { B2_NCCL(ncclGroupEnd()); return B2_OK; }
+
+// Allgather with explicit placement: rank r's counts[r] elements land at recv + offsets[r]
+// (element units).  One grouped set of broadcasts; the local contribution may already sit in
+// place (send == recv + offsets[rank]).  Lets a producer kernel write its slice straight into the
+// gathered buffer and lets callers gather in chunks while the next chunk is being computed
+// (MPIFredholm1: signalprocessing/Fredholm1.py:131-132 gathers only after ALL slices are done).
+extern "C" int b2_allgatherv_at(b2_comm* comm, const void* send, void* recv, const size_t* counts_host,
+                                const size_t* offsets_host, int dtype, void* stream) {
+  if (!comm || !counts_host || !offsets_host) return B2_ERR_ARG;
+  ncclDataType_t dt; size_t mult;
+  if (!map_dtype(dtype, &dt, &mult)) return B2_ERR_DTYPE;
+  const size_t esz = b2_dtype_size(dtype);
+  B2_NCCL(ncclGroupStart());
+  for (int r = 0; r < comm->size; ++r) {
+    if (!counts_host[r]) continue;
+    void* dst = (char*)recv + offsets_host[r] * esz;
+    const void* src = (r == comm->rank) ? send : dst;
+    ncclResult_t res = ncclBroadcast(src, dst, counts_host[r] * mult, dt, r, comm->comm, (cudaStream_t)stream);
+    if (res != ncclSuccess) { ncclGroupEnd(); return 1000 + (int)res; }
+  }
+  B2_NCCL(ncclGroupEnd());
+  return B2_OK;
+}

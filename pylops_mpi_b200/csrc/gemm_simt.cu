@@ -8,6 +8,7 @@
 //     147-167), one slice per blockIdx.z.
 // 64x64 CTA tile, 16-deep K slices through shared memory, 4x4 register tile per
 // thread.  The bf16 tensor-core path lives in gemm_tc.cu.
+#include <string.h>
 #include "common.cuh"
 
 namespace {
@@ -49,11 +50,19 @@ template <> struct Num<c64> {
 
 constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
 
-template <typename T, bool TRANS_A>
+// extra destinations of the SAME logical output buffer in peer GPUs' memory (IPC-mapped, NVLink):
+// the epilogue stores every result element locally and to each peer -> the all-gather of
+// MPIFredholm1 (Fredholm1.py:131-132) happens inside the product kernel, tile by tile.
+struct PeerDst {
+  void* p[8];
+  int n;
+};
+
+template <typename T, bool TRANS_A, bool FUSED = false>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const T* __restrict__ A, size_t lda, size_t sA, const T* __restrict__ B,
                  size_t ldb, size_t sB, T* __restrict__ C, size_t ldc, size_t sC, size_t m,
-                 size_t n, size_t k, bool conj_a, bool accumulate) {
+                 size_t n, size_t k, bool conj_a, bool accumulate, PeerDst peers = PeerDst{}) {
   using N_ = Num<T>;
   __shared__ T As[BK][BM + 1];
   __shared__ T Bs[BK][BN + 1];
@@ -111,7 +120,12 @@ gemm_simt_kernel(const T* __restrict__ A, size_t lda, size_t sA, const T* __rest
       const size_t gj = n0 + tx + 16 * j;
       if (gj >= n) continue;
       T* c = C + gi * ldc + gj;
-      *c = accumulate ? N_::add(*c, acc[i][j]) : acc[i][j];
+      const T v = accumulate ? N_::add(*c, acc[i][j]) : acc[i][j];
+      *c = v;
+      if (FUSED) {
+        const size_t off = (size_t)blockIdx.z * sC + gi * ldc + gj;
+        for (int d = 0; d < peers.n; ++d) reinterpret_cast<T*>(peers.p[d])[off] = v;   // P2P store over NVLink
+      }
     }
   }
 }
@@ -146,6 +160,74 @@ int dispatch(const void* A, size_t lda, size_t sA, const void* B, size_t ldb, si
 }
 
 }  // namespace
+
+template <typename T>
+static int launch_fused(const void* G, const void* x, void* y, void* const* peers, int npeers, size_t nsl, size_t nx,
+                 size_t ny, size_t nz, int adjoint, cudaStream_t st) {
+  const size_t m = adjoint ? ny : nx, k = adjoint ? nx : ny;
+  PeerDst pd;
+  pd.n = npeers;
+  for (int d = 0; d < 8; ++d) pd.p[d] = d < npeers ? peers[d] : nullptr;
+  dim3 grid((unsigned)((nz + BN - 1) / BN), (unsigned)((m + BM - 1) / BM), (unsigned)nsl);
+  if (adjoint)
+    gemm_simt_kernel<T, true, true><<<grid, 256, 0, st>>>((const T*)G, ny, nx * ny, (const T*)x, nz, k * nz, (T*)y, nz,
+                                                          m * nz, m, nz, k, true, false, pd);
+  else
+    gemm_simt_kernel<T, false, true><<<grid, 256, 0, st>>>((const T*)G, ny, nx * ny, (const T*)x, nz, k * nz, (T*)y, nz,
+                                                           m * nz, m, nz, k, false, false, pd);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+// y[s] = op(G[s]) x[s] written to the local output AND to the same offsets of `npeers` peer buffers
+// (fused product + all-gather over NVLink peer memory).  peers_host[d] must already point at the
+// position in peer d's buffer that corresponds to y.
+extern "C" int b2_batched_gemm_allgather(b2_ctx* ctx, const void* G, const void* x, void* y,
+                                         void* const* peers_host, int npeers, size_t nsl, size_t nx, size_t ny,
+                                         size_t nz, int adjoint, int dtype, void* stream) {
+  if (!ctx || npeers < 0 || npeers > 8) return B2_ERR_ARG;
+  if (nsl == 0) return B2_OK;
+  if (!G || !x || !y || (npeers && !peers_host)) return B2_ERR_ARG;
+  if (nsl > 65535) return B2_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case B2_F32: return launch_fused<float>(G, x, y, peers_host, npeers, nsl, nx, ny, nz, adjoint, st);
+    case B2_F64: return launch_fused<double>(G, x, y, peers_host, npeers, nsl, nx, ny, nz, adjoint, st);
+    case B2_C64: return launch_fused<c32>(G, x, y, peers_host, npeers, nsl, nx, ny, nz, adjoint, st);
+    case B2_C128: return launch_fused<c64>(G, x, y, peers_host, npeers, nsl, nx, ny, nz, adjoint, st);
+    default: return B2_ERR_DTYPE;
+  }
+}
+
+// symmetric (peer-mappable) buffers: plain cudaMalloc + CUDA IPC handles exchanged by the caller
+extern "C" int b2_symm_alloc(size_t bytes, void** out) {
+  if (!out) return B2_ERR_ARG;
+  B2_CUDA(cudaMalloc(out, bytes));
+  return B2_OK;
+}
+extern "C" int b2_symm_free(void* p) {
+  if (p) B2_CUDA(cudaFree(p));
+  return B2_OK;
+}
+extern "C" int b2_ipc_get_handle(void* p, void* handle64_host) {
+  if (!p || !handle64_host) return B2_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  B2_CUDA(cudaIpcGetMemHandle(&h, p));
+  memcpy(handle64_host, &h, sizeof h);
+  return B2_OK;
+}
+extern "C" int b2_ipc_open_handle(const void* handle64_host, void** out) {
+  if (!handle64_host || !out) return B2_ERR_ARG;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64_host, sizeof h);
+  B2_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+  return B2_OK;
+}
+extern "C" int b2_ipc_close_handle(void* p) {
+  if (p) B2_CUDA(cudaIpcCloseMemHandle(p));
+  return B2_OK;
+}
 
 extern "C" int b2_gemm(b2_ctx* ctx, const void* A, size_t lda, const void* B, size_t ldb, void* C,
                        size_t ldc, size_t m, size_t n, size_t k, int op_a, int accumulate,

@@ -55,20 +55,67 @@ class MPIFredholm1(MPILinearOperator):
             xl = xl.to(self._tdtype)
         per = nin * self.nz
         xs = xl.reshape(-1)[self.islstart[rank] * per: self.islend[rank] * per]
-        multi = x.size > 1
-        y1 = (torch.empty(self.nsl * nout * self.nz, dtype=self._tdtype, device=xl.device) if multi
-              else y.local_array.view(-1))
-        if self.nsl:
-            _lib.check(_lib.lib.b2_batched_gemm(_lib.ctx(), self.G.data_ptr(), xs.data_ptr(), y1.data_ptr(),
-                                                self.nsl, self.nx, self.ny, self.nz, int(adjoint),
-                                                _lib.code(self._tdtype), _lib.stream()), "b2_batched_gemm")
-        if multi:
-            counts = [n * nout * self.nz for n in self.nsls]
-            allgatherv(x.base_comm, y1, counts, out=y.local_array)
+        pout = nout * self.nz
+        yflat = y.local_array.view(-1)
+        ctx = _lib.ctx()
+        code = _lib.code(self._tdtype)
+
+        def product(s0, s1):
+            """slices [s0, s1) of this rank, written straight into their place in the gathered output"""
+            if s1 <= s0:
+                return
+            G = self.G[s0:s1]
+            xin = xs[s0 * per:s1 * per]
+            yout = yflat[(self.islstart[rank] + s0) * pout:(self.islstart[rank] + s1) * pout]
+            _lib.check(_lib.lib.b2_batched_gemm(ctx, G.data_ptr(), xin.data_ptr(), yout.data_ptr(), s1 - s0,
+                                                self.nx, self.ny, self.nz, int(adjoint), code, _lib.stream()),
+                       "b2_batched_gemm")
+
+        if x.size == 1:
+            product(0, self.nsl)
+            return y
+        # chunked: gather chunk c over NVLink (side stream) while chunk c+1 is being computed
+        import ctypes as C
+        comm = x.base_comm
+        nchunk = 4 if min(self.nsls) >= 8 else 1
+        bounds = [[(c * n) // nchunk for c in range(nchunk + 1)] for n in self.nsls]
+        main = torch.cuda.current_stream()
+        side = _side_stream(xl.device)
+        comm.nccl
+        for c in range(nchunk):
+            product(bounds[rank][c], bounds[rank][c + 1])
+            ev = torch.cuda.Event()
+            ev.record(main)
+            counts = (C.c_size_t * comm.size)(*[(bounds[r][c + 1] - bounds[r][c]) * pout for r in range(comm.size)])
+            offs = (C.c_size_t * comm.size)(*[(int(self.islstart[r]) + bounds[r][c]) * pout for r in range(comm.size)])
+            mine = yflat[(int(self.islstart[rank]) + bounds[rank][c]) * pout:]
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                _lib.check(_lib.lib.b2_allgatherv_at(comm.nccl, mine.data_ptr(), yflat.data_ptr(), counts, offs, code,
+                                                     _lib.stream()), "b2_allgatherv_at")
+        done = torch.cuda.Event()
+        done.record(side)
+        main.wait_event(done)
         return y
 
-    def _matvec(self, x: DistributedArray) -> DistributedArray:
-        return self._apply(x, False)
 
-    def _rmatvec(self, x: DistributedArray) -> DistributedArray:
-        return self._apply(x, True)
+_SIDE = {}
+
+
+def _side_stream(device):
+    st = _SIDE.get(device)
+    if st is None:
+        st = _SIDE[device] = torch.cuda.Stream(device=device)
+    return st
+
+
+def _fr_matvec(self, x: DistributedArray) -> DistributedArray:
+    return self._apply(x, False)
+
+
+def _fr_rmatvec(self, x: DistributedArray) -> DistributedArray:
+    return self._apply(x, True)
+
+
+MPIFredholm1._matvec = _fr_matvec
+MPIFredholm1._rmatvec = _fr_rmatvec

@@ -241,8 +241,10 @@ for ny, nx in [(11, 11), (31, 11)]:
     xo, istop_o, iit_o, r1o, r2o, cost_o = o.cgls(mv, rmv, mv(o.SimArray(o.to_dist(xt, P))),
                                                   o.SimArray(o.to_dist(np.zeros(P * nx), P)), niter=nx, tol=1e-5)
     assert (istop, iit) == (istop_o, iit_o)
-    check("cgls x", host(xinv.local_array), xo.locs[rank], 1e-6, 1e-8)
-    check("cgls cost", cost, cost_o, 1e-5, 1e-8)
+    # rank-1 + 1e-5*I blocks scaled by (r+1)^2: the late, tiny residuals are rounding-sensitive ->
+    # tolerance relative to the initial residual (1e-6 of the problem scale)
+    check("cgls x", host(xinv.local_array), xo.locs[rank], 1e-6, 1e-6 * np.abs(xt).max())
+    check("cgls cost", cost, cost_o, 1e-5, 1e-7 * cost_o[0])
 
 comm.Barrier()
 torch.cuda.synchronize()
