@@ -476,7 +476,14 @@ def run_extras(pm, L, comm, peaks, args):
     xm.local_array.normal_()
     ms = time_loop(lambda: Fr.matvec(xm), K, W, comm)
     fl = 8.0 * nsl * size * ns * nr * nv
-    out["fredholm1_c64_64x256x256x64_per_gpu"] = {"GF/s": fl * K / (ms * 1e-3) / 1e9, "us": ms / K * 1e3}
+    out["fredholm1_c64_64x256x256x64_per_gpu"] = {"GF/s": fl * K / (ms * 1e-3) / 1e9, "us": ms / K * 1e3,
+                                                  "mode": "product kernels + chunked NCCL gather on a side stream"}
+    if size > 1:
+        Ff = pm.MPIFredholm1(G, nz=nv, dtype=np.complex64, fused=True)
+        ms = time_loop(lambda: Ff.matvec(xm), K, W, comm)
+        out["fredholm1_fused_peer_c64_64x256x256x64_per_gpu"] = {
+            "GF/s": fl * K / (ms * 1e-3) / 1e9, "us": ms / K * 1e3,
+            "mode": "ONE kernel: product + all-gather via P2P stores into IPC-mapped peer buffers"}
     return out
 
 

@@ -16,7 +16,7 @@ from ..LinearOperator import MPILinearOperator
 
 class MPIFredholm1(MPILinearOperator):
     def __init__(self, G, nz: int = 1, saveGt: bool = False, usematmul: bool = True,
-                 base_comm=COMM_WORLD, dtype="float64") -> None:
+                 base_comm=COMM_WORLD, dtype="float64", fused: bool = False) -> None:
         base_comm = resolve(base_comm)
         self.nz = int(nz)
         if not isinstance(G, torch.Tensor):
@@ -41,11 +41,73 @@ class MPIFredholm1(MPILinearOperator):
         # not its result; the batched kernel applies G^H on the fly.
         self.saveGt = saveGt
         self.usematmul = usematmul
+        # fused=True: product + all-gather in ONE kernel over NVLink peer memory (IPC-mapped output
+        # arenas); default: product kernels + chunked NCCL gather overlapped on a side stream
+        self._fused = bool(fused) and base_comm.Get_size() > 1
+        if self._fused:
+            self._setup_arenas(base_comm)
+
+    # ---- fused product + all-gather over peer memory ------------------------------------------------
+    def _setup_arenas(self, comm):
+        import ctypes as C
+        esz = torch.empty(0, dtype=self._tdtype).element_size()
+        self._arena = {}
+        nsltot = int(sum(self.nsls))
+        for adjoint in (False, True):
+            nelem = nsltot * (self.ny if adjoint else self.nx) * self.nz
+            for b in range(2):
+                ptr = C.c_void_p()
+                _lib.check(_lib.lib.b2_symm_alloc(max(nelem * esz, 16), C.byref(ptr)), "b2_symm_alloc")
+                h = (C.c_char * 64)()
+                _lib.check(_lib.lib.b2_ipc_get_handle(ptr, h), "b2_ipc_get_handle")
+                handles = comm.allgather(bytes(h.raw))
+                peers = []
+                for r, raw in enumerate(handles):
+                    if r == comm.Get_rank():
+                        peers.append(ptr.value)
+                    else:
+                        q = C.c_void_p()
+                        buf = (C.c_char * 64).from_buffer_copy(raw)
+                        _lib.check(_lib.lib.b2_ipc_open_handle(buf, C.byref(q)), "b2_ipc_open_handle")
+                        peers.append(q.value)
+                self._arena[(adjoint, b)] = (ptr.value, peers, nelem)
+        self._toggle = {False: 0, True: 0}
+        self._flag = torch.zeros(1, dtype=torch.float32, device="cuda")
+
+    def _apply_fused(self, x: DistributedArray, adjoint: bool) -> DistributedArray:
+        import ctypes as C
+        from ..Distributed import allreduce_
+        rank, comm = self.rank, x.base_comm
+        nin, nout = (self.nx, self.ny) if adjoint else (self.ny, self.nx)
+        xl = x.local_array if x.local_array.dtype == self._tdtype else x.local_array.to(self._tdtype)
+        per, pout = nin * self.nz, nout * self.nz
+        xs = xl.reshape(-1)[self.islstart[rank] * per: self.islend[rank] * per]
+        b = self._toggle[adjoint]
+        self._toggle[adjoint] = 1 - b
+        base, peers, nelem = self._arena[(adjoint, b)]
+        esz = xl.element_size()
+        off = int(self.islstart[rank]) * pout * esz
+        others = [peers[r] + off for r in range(comm.Get_size()) if r != rank]
+        arr = (C.c_void_p * len(others))(*others)
+        _lib.check(_lib.lib.b2_batched_gemm_allgather(_lib.ctx(), self.G.data_ptr(), xs.data_ptr(), base + off, arr,
+                                                      len(others), self.nsl, self.nx, self.ny, self.nz, int(adjoint),
+                                                      _lib.code(self._tdtype), _lib.stream()), "b2_batched_gemm_allgather")
+        # stream-ordered cross-rank completion: when this tiny Allreduce finishes every rank's product
+        # kernel (and its peer stores) has finished
+        allreduce_(comm, self._flag, "sum")
+        y = DistributedArray(global_shape=self.shape[1] if adjoint else self.shape[0], base_comm=comm,
+                             partition=x.partition, dtype=self._tdtype)
+        # copy out of the (double-buffered) arena: the caller owns an ordinary array, as in the reference
+        _lib.check(_lib.lib.b2_lincomb(_lib.ctx(), y.local_array.data_ptr(), _lib.cpair(1.0), base, None, None, nelem,
+                                       _lib.code(self._tdtype), 0, _lib.stream()), "b2_lincomb")
+        return y
 
     def _apply(self, x: DistributedArray, adjoint: bool) -> DistributedArray:
         if x.partition not in [Partition.BROADCAST, Partition.UNSAFE_BROADCAST]:
             raise ValueError(f"x should have partition={Partition.BROADCAST},{Partition.UNSAFE_BROADCAST}"
                              f"Got  {x.partition} instead...")
+        if self._fused:
+            return self._apply_fused(x, adjoint)
         rank = self.rank
         nin, nout = (self.nx, self.ny) if adjoint else (self.ny, self.nx)
         y = DistributedArray(global_shape=self.shape[1] if adjoint else self.shape[0],

@@ -225,6 +225,11 @@ for nz in (5, 1):
         refy = o.fredholm1(G_loc, xv.ravel().astype(G.dtype), nz)
         check("fredholm", host(y.local_array), refy, 1e-5, 0)
         check("fredholmH", host((Fr.H @ y).local_array), o.fredholm1(G_loc, refy, nz, adjoint=True), 1e-4, 0)
+        Ff = pm.MPIFredholm1(G_loc[rank].astype(dtype), nz=nz, dtype=dtype, fused=True)   # product + gather in one kernel
+        for _ in range(3):   # repeated applies exercise the double-buffered peer arenas
+            yf = Ff @ xd
+            check("fredholm fused", host(yf.local_array), refy, 1e-5, 0)
+            check("fredholmH fused", host((Ff.H @ yf).local_array), o.fredholm1(G_loc, refy, nz, adjoint=True), 1e-4, 0)
 
 # ---- CGLS on BlockDiag (test_solver.py:150-196) vs oracle at the same P ---------------------------------
 for ny, nx in [(11, 11), (31, 11)]:
