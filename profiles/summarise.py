@@ -80,7 +80,7 @@ def main():
             lines.append(f"| `{name}` | {us:.1f} | {rd / 1e6:.1f} MB | {wr / 1e6:.1f} MB | {float(d['dram_pct_of_ncu_peak'][0]):.1f} | "
                          f"{float(d.get('tensor_pipe_pct', ('0', ''))[0]):.1f} | {float(d['warps_active_pct'][0]):.1f} | "
                          f"{d['regs'][0]} | {d['grid'][0]} x {d['block'][0]} |")
-            if "stencil_vec_kernel<float, 10>" in d["kernel"]:
+            if "stencil_vec_kernel<float, 10" in d["kernel"]:
                 traffic.setdefault("stencil_samples", []).append(rd + wr)
         lines.append("")
     if traffic.get("stencil_samples"):
