@@ -42,7 +42,7 @@ enum { B2_OK = 0, B2_ERR_DTYPE = 2001, B2_ERR_ARG = 2002, B2_ERR_HALO = 2003,
 
 typedef struct b2_ctx b2_ctx;    /* per-device context: SM count, reduction workspace */
 typedef struct b2_comm b2_comm;  /* one NCCL communicator (world, mask group, grid row / col) */
-typedef struct b2_gemm_plan b2_gemm_plan;
+typedef struct b2_peer b2_peer;  /* peer-memory mailbox group for one-shot scalar all-reduces */
 
 int b2_version(void);
 const char* b2_strerror(int code);
@@ -149,6 +149,14 @@ int b2_symm_free(void* p);
 int b2_ipc_get_handle(void* p, void* handle64_host);
 int b2_ipc_open_handle(const void* handle64_host, void** out);
 int b2_ipc_close_handle(void* p);
+
+/* One-shot all-reduce of k <= 8 float64 scalars over NVLink peer memory (no NCCL): the collective half
+ * of DistributedArray.dot / norm (DistributedArray.py:684-686, 714-757) and of the CGLS step scalars.
+ * slots_host[r] = rank r's mailbox (b2_symm_alloc of b2_peer_slots_bytes(), IPC-mapped here). */
+size_t b2_peer_slots_bytes(void);
+int b2_peer_create(int rank, int size, void* const* slots_host, b2_peer** out);
+int b2_peer_destroy(b2_peer* peer);
+int b2_peer_allreduce(b2_peer* peer, double* vals_dev, int k, int op, void* stream);
 
 /* ---- NCCL collectives (utils/_nccl.py:98-403, utils/_mpi.py:21-344,
  *      Distributed.py:35-349) --------------------------------------------- */

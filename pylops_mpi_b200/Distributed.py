@@ -30,6 +30,13 @@ def allreduce_(comm: Comm, buf: torch.Tensor, op: str = SUM) -> torch.Tensor:
     if comm.size == 1 or buf.numel() == 0:
         return buf
     _flat(buf)
+    if buf.dtype is torch.float64 and buf.numel() <= 8:
+        # scalars (dot / norm / solver step lengths): one-shot all-reduce over NVLink peer memory
+        peer = comm.peer
+        if peer is not None:
+            _lib.check(_lib.lib.b2_peer_allreduce(peer, buf.data_ptr(), buf.numel(), _OPS[op], _lib.stream()),
+                       "b2_peer_allreduce")
+            return buf
     _lib.check(_lib.lib.b2_allreduce(comm.nccl, buf.data_ptr(), buf.data_ptr(), buf.numel(),
                                      _lib.code(buf.dtype), _OPS[op], _lib.stream()), "b2_allreduce")
     return buf

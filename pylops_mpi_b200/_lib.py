@@ -89,6 +89,10 @@ def _load():
         "b2_ipc_get_handle": ([vp, vp], i),
         "b2_ipc_open_handle": ([vp, C.POINTER(vp)], i),
         "b2_ipc_close_handle": ([vp], i),
+        "b2_peer_slots_bytes": ([], sz),
+        "b2_peer_create": ([i, i, C.POINTER(vp), C.POINTER(vp)], i),
+        "b2_peer_destroy": ([vp], i),
+        "b2_peer_allreduce": ([vp, vp, i, i, vp], i),
         "b2_get_unique_id": ([vp], i),
         "b2_comm_create": ([i, i, vp, i, C.POINTER(vp)], i),
         "b2_comm_split": ([vp, i, i, C.POINTER(vp)], i),

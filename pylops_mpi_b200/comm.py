@@ -124,6 +124,47 @@ class Comm:
             self._nccl = h
         return self._nccl
 
+    @property
+    def peer(self):
+        """b2_peer handle: IPC-mapped mailboxes for one-shot scalar all-reduces over NVLink peer
+        memory (collective lazy setup; None when unavailable -> callers use NCCL)."""
+        if self._size == 1 or self._size > 8 or os.environ.get("B2_PEER_ALLREDUCE", "1") == "0":
+            return None
+        if getattr(self, "_peer", None) is None and not getattr(self, "_peer_failed", False):
+            from . import _lib
+            ok, ptr, mine = 1, C.c_void_p(), b""
+            try:
+                nbytes = _lib.lib.b2_peer_slots_bytes()
+                _lib.check(_lib.lib.b2_symm_alloc(nbytes, C.byref(ptr)), "b2_symm_alloc")
+                h = (C.c_char * 64)()
+                _lib.check(_lib.lib.b2_ipc_get_handle(ptr, h), "b2_ipc_get_handle")
+                mine = bytes(h.raw)
+            except Exception:
+                ok = 0
+            handles = self.allgather((ok, mine))
+            slots = (C.c_void_p * self._size)()
+            if all(hh[0] for hh in handles):
+                try:
+                    for r, (_, raw) in enumerate(handles):
+                        if r == self._rank:
+                            slots[r] = ptr.value
+                        else:
+                            q = C.c_void_p()
+                            _lib.check(_lib.lib.b2_ipc_open_handle((C.c_char * 64).from_buffer_copy(raw), C.byref(q)),
+                                       "b2_ipc_open_handle")
+                            slots[r] = q.value
+                    hnd = C.c_void_p()
+                    _lib.check(_lib.lib.b2_peer_create(self._rank, self._size, slots, C.byref(hnd)), "b2_peer_create")
+                except Exception:
+                    ok = 0
+            else:
+                ok = 0
+            if min(self.allgather(ok)) == 1:      # every rank zeroed its mailbox and mapped its peers
+                self._peer = hnd
+            else:
+                self._peer_failed = True
+        return getattr(self, "_peer", None)
+
     def split_by_mask(self, mask: Sequence[int]) -> "Comm":
         """cached ``Split(color=mask[rank], key=rank)`` (DistributedArray.py:74-100)"""
         key = tuple(int(m) for m in mask)

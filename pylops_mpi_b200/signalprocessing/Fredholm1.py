@@ -16,7 +16,7 @@ from ..LinearOperator import MPILinearOperator
 
 class MPIFredholm1(MPILinearOperator):
     def __init__(self, G, nz: int = 1, saveGt: bool = False, usematmul: bool = True,
-                 base_comm=COMM_WORLD, dtype="float64", fused: bool = False) -> None:
+                 base_comm=COMM_WORLD, dtype="float64", fused=None) -> None:
         base_comm = resolve(base_comm)
         self.nz = int(nz)
         if not isinstance(G, torch.Tensor):
@@ -43,6 +43,9 @@ class MPIFredholm1(MPILinearOperator):
         self.usematmul = usematmul
         # fused=True: product + all-gather in ONE kernel over NVLink peer memory (IPC-mapped output
         # arenas); default: product kernels + chunked NCCL gather overlapped on a side stream
+        # fused=None (default): on when CUDA IPC peer mapping works between the ranks (probed by comm.peer)
+        if fused is None:
+            fused = base_comm.Get_size() > 1 and base_comm.peer is not None
         self._fused = bool(fused) and base_comm.Get_size() > 1
         if self._fused:
             self._setup_arenas(base_comm)
@@ -72,7 +75,7 @@ class MPIFredholm1(MPILinearOperator):
                         peers.append(q.value)
                 self._arena[(adjoint, b)] = (ptr.value, peers, nelem)
         self._toggle = {False: 0, True: 0}
-        self._flag = torch.zeros(1, dtype=torch.float32, device="cuda")
+        self._flag = torch.zeros(1, dtype=torch.float64, device="cuda")   # float64 -> peer-memory all-reduce
 
     def _apply_fused(self, x: DistributedArray, adjoint: bool) -> DistributedArray:
         import ctypes as C
@@ -139,7 +142,7 @@ class MPIFredholm1(MPILinearOperator):
         # chunked: gather chunk c over NVLink (side stream) while chunk c+1 is being computed
         import ctypes as C
         comm = x.base_comm
-        nchunk = 4 if min(self.nsls) >= 8 else 1
+        nchunk = 1   # measured (profiles/): 4 chunked gathers were slower than one (NCCL launch latency)
         bounds = [[(c * n) // nchunk for c in range(nchunk + 1)] for n in self.nsls]
         main = torch.cuda.current_stream()
         side = _side_stream(xl.device)
