@@ -376,11 +376,12 @@ extern "C" int b2_gemm_bf16(b2_ctx* ctx, const void* A, size_t lda, const void* 
   // TMA: 16-byte aligned bases, row pitches multiple of 16 bytes
   if (!b2_aligned16(A) || !b2_aligned16(B) || (lda % 8) || (ldb % 8)) return B2_ERR_ALIGN;
   {
-    // kernel selection: B2_GEMM_2CTA=1 -> cta_group::2 pair kernel (gemm_tc2.cu), 0 -> 1-CTA kernel
+    // kernel selection: default = cta_group::2 pair kernel (gemm_tc2.cu, 1.49 PF/s at 8192^3);
+    // B2_GEMM_2CTA=0 -> the 1-CTA kernel below (1.33 PF/s), also used when m <= 128
     static int use2 = -1;
     if (use2 < 0) {
       const char* e = getenv("B2_GEMM_2CTA");
-      use2 = e ? atoi(e) : 0;
+      use2 = e ? atoi(e) : 1;
     }
     if (use2 && m > BM) return b2_gemm_bf16_2cta(ctx, A, lda, B, ldb, C, ldc, m, n, k, op_a, accumulate, st);
   }

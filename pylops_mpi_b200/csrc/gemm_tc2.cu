@@ -171,12 +171,14 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (uint32_t s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 2);      // leader: its own producer + the peer's producer (+ tx bytes of both)
+      mbar_init(&full_bar[s], 1);      // leader: ONE arrive.expect_tx for the bytes of BOTH CTAs; the peer's TMA
+                                       // only completes tx bytes (a blocking remote release-arrive per stage
+                                       // from the peer's producer paced the whole pipeline: 721 TF/s)
       mbar_init(&empty_bar[s], 1);     // multicast commit from the leader's MMA thread
     }
     for (uint32_t s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);      // multicast commit
-      mbar_init(&tmem_empty_bar[s], 256);   // leader only: 128 epilogue threads of each CTA
+      mbar_init(&tmem_empty_bar[s], 8);     // leader only: 4 epilogue warps of each CTA (one arrive per warp)
     }
     fence_barrier_init();
   }
@@ -200,7 +202,6 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           uint8_t* sb = sa + A_STAGE_BYTES;
           const uint32_t leader_full = mapa(smem_u32(&full_bar[stage]), 0);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
-          else mbar_arrive_cluster(leader_full);
           if (!A_MN) {
             tma_load_2d_2sm(sa, &tmA, leader_full, (int32_t)(kb * BK), m0);
           } else {
@@ -285,7 +286,8 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         }
       }
       tcgen05_fence_before();
-      mbar_arrive_cluster(mapa(smem_u32(&tmem_empty_bar[acc]), 0));   // the leader's MMA thread waits on it
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa(smem_u32(&tmem_empty_bar[acc]), 0));   // leader's MMA thread waits
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }

@@ -364,12 +364,14 @@ def test_gemm_bf16_alignment_error_is_loud(L):
     assert rc == 2006
 
 
-def test_gemm_bf16_2cta_variant():
-    """cta_group::2 kernel (selected by B2_GEMM_2CTA=1, latched at first use -> own process)"""
+@pytest.mark.parametrize("variant", ["0", "1"])
+def test_gemm_bf16_kernel_variants(variant):
+    """both tensor-core kernels on every shape: B2_GEMM_2CTA=1 (cta_group::2 pair, the default) and
+    B2_GEMM_2CTA=0 (1-CTA); the choice is latched at first use -> own process"""
     import os
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, os.path.join(here, "gemm2cta_worker.py")], capture_output=True, text=True,
-                       timeout=240, env=dict(os.environ, B2_GEMM_2CTA="1"))
+                       timeout=240, env=dict(os.environ, B2_GEMM_2CTA=variant))
     assert r.returncode == 0 and "GEMM2CTA_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
