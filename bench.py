@@ -107,24 +107,66 @@ class ClockSampler:
 # --------------------------------------------------------------------------
 # CPU reference arm (oracle port, one process per core)
 # --------------------------------------------------------------------------
-def _cpu_worker(args):
-    rows, ncols, reps, seed = args
+def _cpu_rank_main(conn, rows, ncols, seed):
+    """one simulated CPU rank: owns its row block (created ONCE, outside the timed passes) and applies the
+    reference's per-rank stencil code to it every time the parent says go"""
     import pylops_mpi_oracle as o
     x = np.random.default_rng(seed).standard_normal((rows, ncols), dtype=np.float32)
     flat = [x.ravel()]
-    t0 = time.perf_counter()
-    for _ in range(reps):
+    conn.send("ready")
+    while True:
+        msg = conn.recv()
+        if msg is None:
+            break
+        t0 = time.perf_counter()
         y = o.first_derivative(flat, (rows, ncols), 1.0, "centered", False, 3, False, dtype=np.float32)
-    dt = time.perf_counter() - t0
-    return dt, float(y[0][ncols + 1])
+        conn.send((time.perf_counter() - t0, float(y[0][ncols + 1])))
+
+
+class CpuRanks:
+    """`cores` OS processes, each a simulated rank of the reference's NumPy path"""
+
+    def __init__(self, cores: int, rows_per_proc: int, ncols: int):
+        import multiprocessing as mp
+        ctx = mp.get_context("spawn")
+        self.cores = cores
+        self.conns, self.procs = [], []
+        for i in range(cores):
+            a, b = ctx.Pipe()
+            p = ctx.Process(target=_cpu_rank_main, args=(b, rows_per_proc, ncols, 42 + i), daemon=True)
+            p.start()
+            self.conns.append(a)
+            self.procs.append(p)
+        for c in self.conns:
+            c.recv()
+
+    def step(self) -> float:
+        """one pass: every rank applies the stencil to its block concurrently; wall-clock seconds"""
+        t0 = time.perf_counter()
+        for c in self.conns:
+            c.send("go")
+        for c in self.conns:
+            c.recv()
+        return time.perf_counter() - t0
+
+    def close(self):
+        for c in self.conns:
+            c.send(None)
+        for p in self.procs:
+            p.join(timeout=10)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
 
 def cpu_reference_pass(pool, cores: int, rows_per_proc: int, ncols: int, reps: int = 1):
     """one 'step' of the CPU arm: every process applies the per-rank reference stencil
     (oracle.first_derivative -> FirstDerivative.py:201-219 incl. its temporaries) to its block"""
-    t0 = time.perf_counter()
-    pool.map(_cpu_worker, [(rows_per_proc, ncols, reps, 42 + i) for i in range(cores)])
-    return time.perf_counter() - t0
+    return pool.step()
 
 
 def run_reference_arm(args):
@@ -134,8 +176,7 @@ def run_reference_arm(args):
         return
     cores = min(os.cpu_count() or 1, 64)
     rows_per_proc = 2048           # 64 MiB float32 per process per pass
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
+    with CpuRanks(cores, rows_per_proc, NCOLS) as pool:
         for _ in range(max(1, args.warmup // 2)):
             cpu_reference_pass(pool, cores, rows_per_proc, NCOLS)
         t0 = time.perf_counter()
@@ -301,7 +342,7 @@ def run_gpu_arm(args):
         import multiprocessing as mp
         cores = min(os.cpu_count() or 1, 64)
         rows_per_proc = 2048
-        with mp.get_context("spawn").Pool(cores) as pool:
+        with CpuRanks(cores, rows_per_proc, NCOLS) as pool:
             cpu_reference_pass(pool, cores, rows_per_proc, NCOLS)
             reps = 0
             t0 = time.perf_counter()
