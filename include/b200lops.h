@@ -42,7 +42,8 @@ enum { B2_OK = 0, B2_ERR_DTYPE = 2001, B2_ERR_ARG = 2002, B2_ERR_HALO = 2003,
 
 typedef struct b2_ctx b2_ctx;    /* per-device context: SM count, reduction workspace */
 typedef struct b2_comm b2_comm;  /* one NCCL communicator (world, mask group, grid row / col) */
-typedef struct b2_peer b2_peer;  /* peer-memory mailbox group for one-shot scalar all-reduces */
+typedef struct b2_peer b2_peer;
+typedef struct b2_peer_vec b2_peer_vec;  /* peer-memory mailboxes for one-shot VECTOR all-reduces */  /* peer-memory mailbox group for one-shot scalar all-reduces */
 
 int b2_version(void);
 const char* b2_strerror(int code);
@@ -157,6 +158,15 @@ size_t b2_peer_slots_bytes(void);
 int b2_peer_create(int rank, int size, void* const* slots_host, b2_peer** out);
 int b2_peer_destroy(b2_peer* peer);
 int b2_peer_allreduce(b2_peer* peer, double* vals_dev, int k, int op, void* stream);
+
+/* One-shot SUM all-reduce of a small vector (<= b2_peer_vec_max_bytes()) over peer memory: the array
+ * Allreduce of MPIVStack._rmatvec (VStack.py:146-148) / MatrixMult.py:420-426 in the latency regime.
+ * boxes_host[r] = rank r's mailbox (b2_symm_alloc of b2_peer_vec_bytes(), IPC-mapped here). */
+size_t b2_peer_vec_bytes(void);
+size_t b2_peer_vec_max_bytes(void);
+int b2_peer_vec_create(int rank, int size, void* const* boxes_host, b2_peer_vec** out);
+int b2_peer_vec_destroy(b2_peer_vec* h);
+int b2_peer_vec_allreduce(b2_peer_vec* h, void* buf_dev, size_t n, int dtype, void* stream);
 
 /* ---- NCCL collectives (utils/_nccl.py:98-403, utils/_mpi.py:21-344,
  *      Distributed.py:35-349) --------------------------------------------- */

@@ -36,9 +36,21 @@ for mode in ("peer", "nccl"):
     for _ in range(200): allreduce_(comm, buf)
     e1.record(); torch.cuda.synchronize()
     lat[mode] = comm.allreduce(e0.elapsed_time(e1) / 200 * 1e3, "max")
+vec = {}
+for nel in (10 ** 3, 10 ** 4, 65536):
+    vb = torch.ones(nel, dtype=torch.float32, device="cuda")
+    for mode in ("peer", "nccl"):
+        os.environ["B2_PEER_ALLREDUCE"] = "1" if mode == "peer" else "0"
+        for _ in range(10): allreduce_(comm, vb)
+        torch.cuda.synchronize(); comm.Barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(100): allreduce_(comm, vb)
+        e1.record(); torch.cuda.synchronize()
+        vec[f"{nel}_{mode}"] = round(comm.allreduce(e0.elapsed_time(e1) / 100 * 1e3, "max"), 2)
 chk = torch.full((3,), float(rank + 1), dtype=torch.float64, device="cuda")
 os.environ["B2_PEER_ALLREDUCE"] = "1"
 allreduce_(comm, chk)
 assert abs(chk[0].item() - size * (size + 1) / 2) < 1e-12
 if rank == 0:
-    print("FREDHOLM_US", size, res, "SCALAR_ALLREDUCE_US", lat)
+    print("FREDHOLM_US", size, res, "SCALAR_ALLREDUCE_US", lat, "VECTOR_ALLREDUCE_F32_US", vec)

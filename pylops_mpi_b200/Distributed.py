@@ -17,6 +17,7 @@ from . import _lib
 from .comm import Comm, resolve, SUM, MAX, MIN
 
 _OPS = {SUM: _lib.SUM, MAX: _lib.MAX, MIN: _lib.MIN, None: _lib.SUM}
+_PEER_VEC_MAX = int(_lib.lib.b2_peer_vec_max_bytes())
 
 
 def _flat(t: torch.Tensor) -> torch.Tensor:
@@ -36,6 +37,14 @@ def allreduce_(comm: Comm, buf: torch.Tensor, op: str = SUM) -> torch.Tensor:
         if peer is not None:
             _lib.check(_lib.lib.b2_peer_allreduce(peer, buf.data_ptr(), buf.numel(), _OPS[op], _lib.stream()),
                        "b2_peer_allreduce")
+            return buf
+    if op in (SUM, None) and buf.dtype in (torch.float32, torch.float64) and \
+            buf.numel() * buf.element_size() <= _PEER_VEC_MAX and buf.data_ptr() % 16 == 0:
+        # latency regime (e.g. MPIVStack adjoint with a small model): one-shot all-reduce over peer memory
+        pv = comm.peer_vec
+        if pv is not None:
+            _lib.check(_lib.lib.b2_peer_vec_allreduce(pv, buf.data_ptr(), buf.numel(), _lib.code(buf.dtype),
+                                                      _lib.stream()), "b2_peer_vec_allreduce")
             return buf
     _lib.check(_lib.lib.b2_allreduce(comm.nccl, buf.data_ptr(), buf.data_ptr(), buf.numel(),
                                      _lib.code(buf.dtype), _OPS[op], _lib.stream()), "b2_allreduce")

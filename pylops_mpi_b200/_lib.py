@@ -93,6 +93,11 @@ def _load():
         "b2_peer_create": ([i, i, C.POINTER(vp), C.POINTER(vp)], i),
         "b2_peer_destroy": ([vp], i),
         "b2_peer_allreduce": ([vp, vp, i, i, vp], i),
+        "b2_peer_vec_bytes": ([], sz),
+        "b2_peer_vec_max_bytes": ([], sz),
+        "b2_peer_vec_create": ([i, i, C.POINTER(vp), C.POINTER(vp)], i),
+        "b2_peer_vec_destroy": ([vp], i),
+        "b2_peer_vec_allreduce": ([vp, vp, sz, i, vp], i),
         "b2_get_unique_id": ([vp], i),
         "b2_comm_create": ([i, i, vp, i, C.POINTER(vp)], i),
         "b2_comm_split": ([vp, i, i, C.POINTER(vp)], i),

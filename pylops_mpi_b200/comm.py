@@ -124,17 +124,16 @@ class Comm:
             self._nccl = h
         return self._nccl
 
-    @property
-    def peer(self):
-        """b2_peer handle: IPC-mapped mailboxes for one-shot scalar all-reduces over NVLink peer
-        memory (collective lazy setup; None when unavailable -> callers use NCCL)."""
+    def _ipc_mailboxes(self, attr: str, nbytes_fn: str, create_fn: str):
+        """collective lazy setup of an IPC-mapped mailbox group (one symmetric buffer per rank, every
+        rank maps every peer's); returns the library handle or None when CUDA IPC is unavailable"""
         if self._size == 1 or self._size > 8 or os.environ.get("B2_PEER_ALLREDUCE", "1") == "0":
             return None
-        if getattr(self, "_peer", None) is None and not getattr(self, "_peer_failed", False):
+        if getattr(self, attr, None) is None and not getattr(self, attr + "_failed", False):
             from . import _lib
-            ok, ptr, mine = 1, C.c_void_p(), b""
+            ok, ptr, mine, hnd = 1, C.c_void_p(), b"", None
             try:
-                nbytes = _lib.lib.b2_peer_slots_bytes()
+                nbytes = getattr(_lib.lib, nbytes_fn)()
                 _lib.check(_lib.lib.b2_symm_alloc(nbytes, C.byref(ptr)), "b2_symm_alloc")
                 h = (C.c_char * 64)()
                 _lib.check(_lib.lib.b2_ipc_get_handle(ptr, h), "b2_ipc_get_handle")
@@ -142,28 +141,38 @@ class Comm:
             except Exception:
                 ok = 0
             handles = self.allgather((ok, mine))
-            slots = (C.c_void_p * self._size)()
+            boxes = (C.c_void_p * self._size)()
             if all(hh[0] for hh in handles):
                 try:
                     for r, (_, raw) in enumerate(handles):
                         if r == self._rank:
-                            slots[r] = ptr.value
+                            boxes[r] = ptr.value
                         else:
                             q = C.c_void_p()
                             _lib.check(_lib.lib.b2_ipc_open_handle((C.c_char * 64).from_buffer_copy(raw), C.byref(q)),
                                        "b2_ipc_open_handle")
-                            slots[r] = q.value
+                            boxes[r] = q.value
                     hnd = C.c_void_p()
-                    _lib.check(_lib.lib.b2_peer_create(self._rank, self._size, slots, C.byref(hnd)), "b2_peer_create")
+                    _lib.check(getattr(_lib.lib, create_fn)(self._rank, self._size, boxes, C.byref(hnd)), create_fn)
                 except Exception:
                     ok = 0
             else:
                 ok = 0
             if min(self.allgather(ok)) == 1:      # every rank zeroed its mailbox and mapped its peers
-                self._peer = hnd
+                setattr(self, attr, hnd)
             else:
-                self._peer_failed = True
-        return getattr(self, "_peer", None)
+                setattr(self, attr + "_failed", True)
+        return getattr(self, attr, None)
+
+    @property
+    def peer(self):
+        """b2_peer handle: mailboxes for one-shot SCALAR all-reduces over NVLink peer memory"""
+        return self._ipc_mailboxes("_peer", "b2_peer_slots_bytes", "b2_peer_create")
+
+    @property
+    def peer_vec(self):
+        """b2_peer_vec handle: mailboxes for one-shot small-VECTOR all-reduces over peer memory"""
+        return self._ipc_mailboxes("_peer_vec", "b2_peer_vec_bytes", "b2_peer_vec_create")
 
     def split_by_mask(self, mask: Sequence[int]) -> "Comm":
         """cached ``Split(color=mask[rank], key=rank)`` (DistributedArray.py:74-100)"""

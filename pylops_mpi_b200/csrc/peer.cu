@@ -100,3 +100,114 @@ extern "C" int b2_peer_allreduce(b2_peer* h, double* vals_dev, int k, int op, vo
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
+
+// =====================================================================================
+// One-shot all-reduce (SUM) of a small/medium VECTOR over peer memory: the array Allreduce of
+// MPIVStack._rmatvec (VStack.py:146-148) / block MatrixMult adjoint (MatrixMult.py:420-426) in the
+// latency regime (config 2: n <= ~1e5 floats).  Every rank pushes its vector into its slot of every
+// peer's mailbox with 16-byte P2P stores, the last CTA to finish publishes a system-scope flag on all
+// peers, every CTA then waits for the P flags in its OWN mailbox and folds the P slots in rank order
+// (bit-identical results on all ranks).  Double-buffered by sequence parity like the scalar mailbox.
+// =====================================================================================
+namespace {
+constexpr size_t VEC_SLOT_BYTES = 256 * 1024;          // per (parity, source rank)
+struct VecBox {
+  unsigned long long flag[2][PEER_MAX];
+  unsigned int arrive[2];
+  unsigned int pad[2];
+};
+constexpr size_t VEC_HDR_BYTES = 256;                  // VecBox padded
+static_assert(sizeof(VecBox) <= VEC_HDR_BYTES, "header too small");
+struct VecPtrs {
+  char* p[PEER_MAX];
+};
+__device__ __forceinline__ char* vec_slot(char* base, int par, int src) {
+  return base + VEC_HDR_BYTES + ((size_t)par * PEER_MAX + src) * VEC_SLOT_BYTES;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+peer_allreduce_vec_kernel(VecPtrs pp, int rank, int P, T* __restrict__ buf, size_t n, unsigned long long seq) {
+  const int par = (int)(seq & 1ull);
+  constexpr int V = 16 / sizeof(T);
+  const size_t nvec = n / V;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  // phase 1: push my vector to every peer (including myself)
+  for (int d = 0; d < P; ++d) {
+    T* dst = reinterpret_cast<T*>(vec_slot(pp.p[d], par, rank));
+    for (size_t i = tid; i < nvec; i += nthr)
+      reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(buf)[i];
+    for (size_t i = nvec * V + tid; i < n; i += nthr) dst[i] = buf[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  VecBox* me = reinterpret_cast<VecBox*>(pp.p[rank]);
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&me->arrive[par], 1u);
+    if (t == gridDim.x - 1) {           // last CTA: everything of this rank is on its way -> publish
+      me->arrive[par] = 0u;
+      __threadfence_system();
+      for (int d = 0; d < P; ++d)
+        st_release_sys(&reinterpret_cast<VecBox*>(pp.p[d])->flag[par][rank], seq);
+    }
+  }
+  // phase 2: wait for all P contributions in my own mailbox, fold in rank order
+  if (threadIdx.x < P) {
+    while (ld_acquire_sys(&me->flag[par][threadIdx.x]) < seq) { }
+  }
+  __syncthreads();
+  for (size_t i = tid; i < n; i += nthr) {
+    T acc = *reinterpret_cast<volatile const T*>(reinterpret_cast<const T*>(vec_slot(pp.p[rank], par, 0)) + i);
+    for (int r = 1; r < P; ++r)
+      acc += *reinterpret_cast<volatile const T*>(reinterpret_cast<const T*>(vec_slot(pp.p[rank], par, r)) + i);
+    buf[i] = acc;
+  }
+}
+}  // namespace
+
+struct b2_peer_vec {
+  int rank, size;
+  VecPtrs pp;
+  unsigned long long seq;
+};
+
+extern "C" size_t b2_peer_vec_bytes(void) { return VEC_HDR_BYTES + 2 * PEER_MAX * VEC_SLOT_BYTES; }
+extern "C" size_t b2_peer_vec_max_bytes(void) { return VEC_SLOT_BYTES; }
+
+extern "C" int b2_peer_vec_create(int rank, int size, void* const* boxes_host, b2_peer_vec** out) {
+  if (!out || !boxes_host || size < 1 || size > PEER_MAX || rank < 0 || rank >= size) return B2_ERR_ARG;
+  b2_peer_vec* h = new b2_peer_vec();
+  h->rank = rank;
+  h->size = size;
+  h->seq = 0;
+  for (int r = 0; r < PEER_MAX; ++r) h->pp.p[r] = r < size ? (char*)boxes_host[r] : nullptr;
+  cudaError_t e = cudaMemset(boxes_host[rank], 0, VEC_HDR_BYTES);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { delete h; return (int)e; }
+  *out = h;
+  return B2_OK;
+}
+extern "C" int b2_peer_vec_destroy(b2_peer_vec* h) {
+  delete h;
+  return B2_OK;
+}
+
+// in-place SUM all-reduce of n elements (n * sizeof <= b2_peer_vec_max_bytes()), dtype F32 / F64
+extern "C" int b2_peer_vec_allreduce(b2_peer_vec* h, void* buf_dev, size_t n, int dtype, void* stream) {
+  if (!h || !buf_dev) return B2_ERR_ARG;
+  if (n == 0) return B2_OK;
+  const size_t esz = b2_dtype_size(dtype);
+  if ((dtype != B2_F32 && dtype != B2_F64) || n * esz > VEC_SLOT_BYTES) return B2_ERR_ARG;
+  if (!b2_aligned16(buf_dev)) return B2_ERR_ALIGN;
+  h->seq += 1;
+  // few CTAs: all of them spin on flags, so they must be co-resident (16 << 148 SMs)
+  size_t work = (n * esz + 16 * 256 - 1) / (16 * 256);
+  const unsigned grid = (unsigned)(work < 1 ? 1 : (work > 16 ? 16 : work));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == B2_F32)
+    peer_allreduce_vec_kernel<float><<<grid, 256, 0, st>>>(h->pp, h->rank, h->size, (float*)buf_dev, n, h->seq);
+  else
+    peer_allreduce_vec_kernel<double><<<grid, 256, 0, st>>>(h->pp, h->rank, h->size, (double*)buf_dev, n, h->seq);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}

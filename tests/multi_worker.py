@@ -63,6 +63,21 @@ g = host(G.add_ghost_cells(cells_front=2, cells_back=1))
 ref = o.add_ghost_cells(o.to_dist(np.arange(40.0 * P).reshape(10 * P, 4), P), 0, [2] * P, [1] * P)[rank]
 check("ghost", g, ref, 0, 0)
 
+# ---- array all-reduce: peer-memory one-shot path (small) and NCCL path (large) vs the exact sum --------
+from pylops_mpi_b200.Distributed import allreduce_  # noqa: E402
+for dt in (torch.float32, torch.float64):
+    for nel in (1, 5, 9, 1000, 32768, 65536 if dt is torch.float32 else 32768, 70001, 300000):
+        gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+        v = torch.randint(-1000, 1000, (nel,), device="cuda", generator=gen).to(dt)     # integers: exact sums
+        ref = torch.zeros(nel, dtype=dt, device="cuda")
+        for r in range(P):
+            g2 = torch.Generator(device="cuda").manual_seed(1234 + r)
+            ref += torch.randint(-1000, 1000, (nel,), device="cuda", generator=g2).to(dt)
+        for _ in range(3):                                                              # repeated: parity buffers
+            w = v.clone()
+            allreduce_(comm, w)
+            assert torch.equal(w, ref), f"[rank {rank}] allreduce {dt} n={nel}"
+
 # ---- MPIFirstDerivative (config 1 at P = world size, plus the test_derivative grid) ---------------
 x = np.zeros((11, 21))
 x[5, 10] = 1.0
