@@ -411,13 +411,16 @@ def run_extras(pm, L, comm, peaks, args):
     if size > 1:
         from pylops_mpi_b200.Distributed import allreduce_
         sweep = {}
-        for ne in (10 ** 4, 10 ** 5, 10 ** 6, 10 ** 7, 10 ** 8, 10 ** 9 // 4):
-            buf = a.local_array[:ne]
+        big = torch.zeros(10 ** 9, dtype=torch.float32, device="cuda")      # 4 GB: config 2 sweeps 1e4 .. 1e9 elements
+        for ne in (10 ** 4, 10 ** 5, 10 ** 6, 10 ** 7, 10 ** 8, 10 ** 9):
+            buf = big[:ne]
             ms = time_loop(lambda: allreduce_(comm, buf), 10, 3, comm)
             us = ms / 10 * 1e3
             alg = 4 * ne / (us * 1e-6) / 1e9
-            sweep[str(ne)] = {"us": us, "algbw_GB/s": alg, "busbw_GB/s": alg * 2 * (size - 1) / size}
+            sweep[str(ne)] = {"us": us, "algbw_GB/s": alg, "busbw_GB/s": alg * 2 * (size - 1) / size,
+                              "path": "peer-memory one-shot" if 4 * ne <= 64 * 1024 and comm.peer_vec is not None else "nccl"}
         out["allreduce_f32_sweep"] = sweep
+        del big
     del a, b
 
     # --- config 3: BlockDiag of one 4096^2 f32 block per GPU + cgls ------------------------

@@ -17,7 +17,9 @@ from . import _lib
 from .comm import Comm, resolve, SUM, MAX, MIN
 
 _OPS = {SUM: _lib.SUM, MAX: _lib.MAX, MIN: _lib.MIN, None: _lib.SUM}
-_PEER_VEC_MAX = int(_lib.lib.b2_peer_vec_max_bytes())
+# one-shot peer-memory all-reduce below this payload, NCCL above (measured at 2 GPUs: 10.7 vs 11.1 us at
+# 4 KB, 12.4 vs 13.9 us at 40 KB, 18.7 vs 14.9 us at 256 KB; NCCL needs ~34 us at 8 GPUs for <= 400 KB)
+_PEER_VEC_MAX = min(int(_lib.lib.b2_peer_vec_max_bytes()), 64 * 1024)
 
 
 def _flat(t: torch.Tensor) -> torch.Tensor:
