@@ -102,6 +102,19 @@ int b2_first_derivative(b2_ctx* ctx, const void* x, void* y, const void* halo_lo
                         double sampling, int adjoint, int dtype, void* stream);
 /* rows of halo each side needs (1 or 2) */
 int b2_first_derivative_halo(int kind, int order, int adjoint, int* need_lo, int* need_hi);
+/* MPISecondDerivative per-rank apply (basicoperators/SecondDerivative.py:125-257): same contract as
+ * b2_first_derivative (row block + up to 2 halo rows per side, exact-transpose adjoint), scale 1/sampling^2 */
+int b2_second_derivative(b2_ctx* ctx, const void* x, void* y, const void* halo_lo, int n_lo,
+                         const void* halo_hi, int n_hi, size_t nrows_local, size_t ncols, size_t row0,
+                         size_t nrows_global, int kind, int edge, double sampling, int adjoint, int dtype,
+                         void* stream);
+int b2_second_derivative_halo(int kind, int edge, int adjoint, int* need_lo, int* need_hi);
+/* rank-local first (deriv=1) / second (deriv=2) derivative along the MIDDLE axis of a C-ordered
+ * [n_outer][n_axis][n_inner] block: the non-partitioned directions of MPILaplacian / MPIGradient
+ * (Laplacian.py:97-126, Gradient.py:101-119 wrap a serial pylops derivative per rank) */
+int b2_derivative_axis(b2_ctx* ctx, const void* x, void* y, size_t n_outer, size_t n_axis, size_t n_inner,
+                       int deriv, int kind, int order, int edge, double sampling, int adjoint, int dtype,
+                       void* stream);
 /* Same operator on HOST buffers (pageable or pinned).  x_host / y_host address the
  * GLOBAL [nrows_global x ncols] arrays (to_dist keeps the global array replicated on
  * every rank's host, DistributedArray.py:440-459); this call processes rows

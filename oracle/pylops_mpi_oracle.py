@@ -722,3 +722,146 @@ def cg(matvec: Callable, y: SimArray, x0: SimArray, niter=10, tol=1e-4):
         iiter += 1
         cost.append(float(np.sqrt(kold)))
     return x, iiter, np.array(cost)
+
+
+# --------------------------------------------------------------------------
+# MPISecondDerivative  (basicoperators/SecondDerivative.py)  -- "next" row f2
+# --------------------------------------------------------------------------
+def second_derivative(x_flat: List[np.ndarray], dims: Tuple[int, ...], sampling: float = 1.0,
+                      kind: str = "centered", edge: bool = False, adjoint: bool = False,
+                      dtype=np.float64) -> List[np.ndarray]:
+    """SecondDerivative.py:112-257 applied to a flat SCATTER vector (per-rank list)."""
+    size = len(x_flat)
+    dims = tuple(int(d) for d in (dims if np.ndim(dims) else (dims,)))
+    shapes = local_shapes(dims, size, SCATTER, 0)
+    x = reshaped_in(x_flat, shapes)
+    N = dims[0]
+    last = size - 1
+    y = [np.zeros(s, dtype=dtype) for s in shapes]
+    gh = lambda f, b: add_ghost_cells(x, 0, [f] * size if f is not None else None,   # noqa: E731
+                                      [b] * size if b is not None else None)
+    h2 = sampling ** 2
+    if kind == "forward" and not adjoint:                  # :125-133
+        g = gh(None, 2)
+        for r in range(size):
+            yf = g[r][2:] - 2 * g[r][1:-1] + g[r][:-2]
+            if r == last:
+                yf = np.append(yf, _z(min(N, 2), dims, yf.dtype), axis=0)
+            y[r][:] = yf / h2
+    elif kind == "forward" and adjoint:                    # :135-158
+        g1 = gh(1, 1)
+        g2 = gh(2, None)
+        for r in range(size):
+            if r == last:
+                y[r][:-2] += x[r][:-2]
+            else:
+                y[r][:] += x[r][:]
+            yf = g1[r][:-2]
+            if r == 0:
+                yf = np.append(_z(1, dims, yf.dtype), yf, axis=0)
+            if r == last:
+                yf = np.append(yf, _z(min(1, N - 1), dims, yf.dtype), axis=0)
+            y[r][:] -= 2 * yf
+            yf = g2[r][:-2]
+            if r == 0:
+                yf = np.append(_z(min(N, 2), dims, yf.dtype), yf, axis=0)
+            y[r][:] += yf
+            y[r][:] /= h2
+    elif kind == "backward" and not adjoint:               # :160-168
+        g = gh(2, None)
+        for r in range(size):
+            yb = g[r][2:] - 2 * g[r][1:-1] + g[r][:-2]
+            if r == 0:
+                yb = np.append(_z(min(N, 2), dims, yb.dtype), yb, axis=0)
+            y[r][:] = yb / h2
+    elif kind == "backward" and adjoint:                   # :170-191
+        g1 = gh(None, 2)
+        g2 = gh(1, 1)
+        for r in range(size):
+            yb = g1[r][2:]
+            if r == last:
+                yb = np.append(yb, _z(min(2, N), dims, yb.dtype), axis=0)
+            y[r][:] += yb
+            yb = 2 * g2[r][2:]
+            if r == 0:
+                yb = np.append(_z(1, dims, yb.dtype), yb, axis=0)
+            if r == last:
+                yb = np.append(yb, _z(min(1, N - 1), dims, yb.dtype), axis=0)
+            y[r][:] -= yb
+            if r == 0:
+                y[r][2:] += x[r][2:]
+            else:
+                y[r][:] += x[r][:]
+            y[r][:] /= h2
+    elif kind == "centered" and not adjoint:               # :193-208
+        g = gh(1, 1)
+        for r in range(size):
+            yc = g[r][2:] - 2 * g[r][1:-1] + g[r][:-2]
+            if r == 0:
+                yc = np.append(_z(1, dims, yc.dtype), yc, axis=0)
+            if r == last:
+                yc = np.append(yc, _z(min(1, N - 1), dims, yc.dtype), axis=0)
+            y[r][:] = yc
+            if edge:
+                if r == 0:
+                    y[r][0] = x[r][0] - 2 * x[r][1] + x[r][2]
+                if r == last:
+                    y[r][-1] = x[r][-3] - 2 * x[r][-2] + x[r][-1]
+            y[r][:] /= h2
+    elif kind == "centered" and adjoint:                   # :210-246
+        g1 = gh(None, 2)
+        g2 = gh(1, 1)
+        g3 = gh(2, None)
+        for r in range(size):
+            yc = g1[r][1:-1]
+            if r == last:
+                yc = np.append(yc, _z(min(2, N), dims, yc.dtype), axis=0)
+            y[r][:] += yc
+            yc = 2 * g2[r][1:-1]
+            if r == 0:
+                yc = np.append(_z(1, dims, yc.dtype), yc, axis=0)
+            if r == last:
+                yc = np.append(yc, _z(min(1, N - 1), dims, yc.dtype), axis=0)
+            y[r][:] -= yc
+            yc = g3[r][1:-1]
+            if r == 0:
+                yc = np.append(_z(min(2, N), dims, yc.dtype), yc, axis=0)
+            y[r][:] += yc
+            if edge:
+                if r == 0:
+                    y[r][0] += x[r][0]
+                    y[r][1] -= 2 * x[r][0]
+                    y[r][2] += x[r][0]
+                if r == last:
+                    y[r][-3] += x[r][-1]
+                    y[r][-2] -= 2 * x[r][-1]
+                    y[r][-1] += x[r][-1]
+            y[r][:] /= h2
+    else:
+        raise NotImplementedError("'kind' must be 'forward', 'centered' or 'backward'")
+    return [a.ravel() for a in y]
+
+
+def second_derivative_dense(N: int, sampling=1.0, kind="centered", edge=False) -> np.ndarray:
+    """serial N x N second-derivative matrix along axis 0 (what the reference tests compare with)"""
+    D = np.zeros((N, N))
+    if kind == "forward":
+        for i in range(N - 2):
+            D[i, i], D[i, i + 1], D[i, i + 2] = 1, -2, 1
+    elif kind == "backward":
+        for i in range(2, N):
+            D[i, i - 2], D[i, i - 1], D[i, i] = 1, -2, 1
+    elif kind == "centered":
+        for i in range(1, N - 1):
+            D[i, i - 1], D[i, i], D[i, i + 1] = 1, -2, 1
+        if edge:
+            D[0, 0], D[0, 1], D[0, 2] = 1, -2, 1
+            D[N - 1, N - 3], D[N - 1, N - 2], D[N - 1, N - 1] = 1, -2, 1
+    else:
+        raise NotImplementedError
+    return D / sampling ** 2
+
+
+def derivative_along_axis(x: np.ndarray, axis: int, D: np.ndarray) -> np.ndarray:
+    """apply the dense stencil matrix D along `axis` of x (serial reference for Laplacian terms)"""
+    return np.moveaxis(np.tensordot(D, x, axes=([1], [axis])), 0, axis)

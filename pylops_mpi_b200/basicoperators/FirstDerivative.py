@@ -53,6 +53,18 @@ class MPIFirstDerivative(MPILinearOperator):
             raise NotImplementedError("'kind' must be 'forward', 'centered', or 'backward'")
         self._kind_code = _KINDS[kind]
 
+    # ---- hooks (MPISecondDerivative overrides these two) --------------------------------------------
+    def _halo_need(self, adjoint: bool):
+        need_lo, need_hi = C.c_int(), C.c_int()
+        _lib.check(_lib.lib.b2_first_derivative_halo(self._kind_code, self.order, int(adjoint),
+                                                     C.byref(need_lo), C.byref(need_hi)), "b2_first_derivative_halo")
+        return need_lo.value, need_hi.value
+
+    def _kernel(self, ctx, xp, yp, lop, lo_n, hip, hi_n, nrows, ncols, row0, adjoint, code):
+        _lib.check(_lib.lib.b2_first_derivative(ctx, xp, yp, lop, lo_n, hip, hi_n, nrows, ncols, row0, self.dims[0],
+                                                self._kind_code, self.order, int(self.edge), float(self.sampling),
+                                                adjoint, code, _lib.stream()), "b2_first_derivative")
+
     def _matvec(self, x: DistributedArray) -> DistributedArray:
         if x.partition is Partition.BROADCAST:
             x = DistributedArray.to_dist(x=x.local_array, base_comm=x.base_comm)
@@ -84,12 +96,9 @@ class MPIFirstDerivative(MPILinearOperator):
         cached = self._plan_cache.get(key)
         if cached is None:
             rows = [s[0] for s in x._local_shapes]
-            need_lo, need_hi = C.c_int(), C.c_int()
-            _lib.check(_lib.lib.b2_first_derivative_halo(self._kind_code, self.order, int(adjoint),
-                                                         C.byref(need_lo), C.byref(need_hi)),
-                       "b2_first_derivative_halo")
-            plan = halo_plan(rows, x.rank, need_lo.value, need_hi.value) if x.size > 1 else None
-            cached = self._plan_cache[key] = (rows, offsets(rows)[x.rank], need_lo.value, need_hi.value, plan)
+            need_lo, need_hi = self._halo_need(adjoint)
+            plan = halo_plan(rows, x.rank, need_lo, need_hi) if x.size > 1 else None
+            cached = self._plan_cache[key] = (rows, offsets(rows)[x.rank], need_lo, need_hi, plan)
         rows, row0, nl, nh, plan = cached
         nloc = rows[x.rank]
         ncols = int(np.prod(self.dims[1:])) * mult if len(self.dims) > 1 else mult
@@ -107,12 +116,9 @@ class MPIFirstDerivative(MPILinearOperator):
             """stencil on local rows [r_begin, r_end) with explicit halo tensors"""
             if r_end <= r_begin:
                 return
-            _lib.check(_lib.lib.b2_first_derivative(
-                ctx, xr[r_begin:].data_ptr(), yr[r_begin:].data_ptr(),
-                lo_t.data_ptr() if lo_n else None, lo_n, hi_t.data_ptr() if hi_n else None, hi_n,
-                r_end - r_begin, ncols, row0 + r_begin, self.dims[0], self._kind_code, self.order,
-                int(self.edge), float(self.sampling), int(adjoint), code, _lib.stream()),
-                "b2_first_derivative")
+            self._kernel(ctx, xr[r_begin:].data_ptr(), yr[r_begin:].data_ptr(),
+                         lo_t.data_ptr() if lo_n else None, lo_n, hi_t.data_ptr() if hi_n else None, hi_n,
+                         r_end - r_begin, ncols, row0 + r_begin, int(adjoint), code)
 
         if x.size == 1:
             launch(0, nloc, None, 0, None, 0)

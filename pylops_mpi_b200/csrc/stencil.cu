@@ -35,12 +35,30 @@ struct StencilParams {
   double scale;                // 1/sampling
   long long nloc, ncols, row0, nglob;
   int n_lo, n_hi;
+  long long batch_stride;      // elements between consecutive [nloc x ncols] problems (local axis-k derivatives)
+  int nbatch;
 };
 
 // forward taps of global row i (offsets -2..2), before the 1/sampling scale
-void fwd_taps(long long i, long long N, int kind, int order, int edge, double t[NT]) {
+// second-derivative taps (MPISecondDerivative, basicoperators/SecondDerivative.py:125-257)
+void fwd_taps2(long long i, long long N, int kind, int edge, double t[NT]) {
+  if (kind == B2_FD_FORWARD) {            // y[i] = x[i] - 2 x[i+1] + x[i+2], i <= N-3      (:128-133)
+    if (i <= N - 3) { t[R] = 1.0; t[R + 1] = -2.0; t[R + 2] = 1.0; }
+  } else if (kind == B2_FD_BACKWARD) {    // y[i] = x[i-2] - 2 x[i-1] + x[i], i >= 2       (:160-165)
+    if (i >= 2) { t[R - 2] = 1.0; t[R - 1] = -2.0; t[R] = 1.0; }
+  } else {                                // centered                                      (:193-208)
+    if (i >= 1 && i <= N - 2) { t[R - 1] = 1.0; t[R] = -2.0; t[R + 1] = 1.0; }
+    else if (edge && N >= 3) {
+      if (i == 0) { t[R] = 1.0; t[R + 1] = -2.0; t[R + 2] = 1.0; }
+      if (i == N - 1) { t[R - 2] = 1.0; t[R - 1] = -2.0; t[R] = 1.0; }
+    }
+  }
+}
+
+void fwd_taps(long long i, long long N, int deriv, int kind, int order, int edge, double t[NT]) {
   for (int k = 0; k < NT; ++k) t[k] = 0.0;
   if (i < 0 || i >= N) return;
+  if (deriv == 2) { fwd_taps2(i, N, kind, edge, t); return; }
   if (kind == B2_FD_FORWARD) {
     if (i <= N - 2) { t[R] = -1.0; t[R + 1] = 1.0; }
   } else if (kind == B2_FD_BACKWARD) {
@@ -68,11 +86,11 @@ void fwd_taps(long long i, long long N, int kind, int order, int edge, double t[
   }
 }
 
-void row_taps(long long i, long long N, int kind, int order, int edge, int adjoint, double t[NT]) {
-  if (!adjoint) { fwd_taps(i, N, kind, order, edge, t); return; }
+void row_taps(long long i, long long N, int deriv, int kind, int order, int edge, int adjoint, double t[NT]) {
+  if (!adjoint) { fwd_taps(i, N, deriv, kind, order, edge, t); return; }
   for (int k = -R; k <= R; ++k) {
     double f[NT];
-    fwd_taps(i + k, N, kind, order, edge, f);   // zero outside [0, N)
+    fwd_taps(i + k, N, deriv, kind, order, edge, f);   // zero outside [0, N)
     t[k + R] = f[-k + R];
   }
 }
@@ -109,6 +127,8 @@ stencil_vec_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restri
   // 1-D grid, column tile fastest: concurrently running CTAs cover whole rows
   const long long n_ct = (ncv + ST_COLS - 1) / ST_COLS;
   const long long ct = (long long)blockIdx.x % n_ct, rc = (long long)blockIdx.x / n_ct;
+  x += (size_t)blockIdx.y * (size_t)p.batch_stride;     // batched local problems (blockIdx.y = 0 otherwise)
+  y += (size_t)blockIdx.y * (size_t)p.batch_stride;
   const long long cv = ct * ST_COLS + threadIdx.x;
   const long long r0 = rc * ST_ROWS;
   const long long r1 = (r0 + ST_ROWS < p.nloc) ? r0 + ST_ROWS : p.nloc;
@@ -196,12 +216,18 @@ stencil_vec_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restri
 // -------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
-stencil_generic_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restrict__ lo,
+stencil_generic_kernel(const T* x, T* y, const T* __restrict__ lo,
                        const T* __restrict__ hi, const __grid_constant__ StencilParams p) {
-  const size_t total = (size_t)p.nloc * (size_t)p.ncols;
+  const size_t per = (size_t)p.nloc * (size_t)p.ncols;
+  const size_t total = per * (size_t)p.nbatch;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const T scale = (T)p.scale;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+  const T* x0 = x;
+  T* y0 = y;
+  for (size_t gidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; gidx < total; gidx += stride) {
+    const size_t b = gidx / per, idx = gidx - b * per;
+    x = x0 + b * (size_t)p.batch_stride;
+    y = y0 + b * (size_t)p.batch_stride;
     const long long r = (long long)(idx / (size_t)p.ncols);
     const long long j = (long long)(idx - (size_t)r * (size_t)p.ncols);
     const long long gi = p.row0 + r;
@@ -232,7 +258,8 @@ int launch_vec(const void* x, void* y, const void* lo, const void* hi, const Ste
   constexpr int V = Vec16<T>::N;
   const long long nblk = ((p.ncols / V + COLS - 1) / COLS) * ((p.nloc + ROWS - 1) / ROWS);
   if (nblk > 0x7fffffffLL) return B2_ERR_ARG;
-  const unsigned grid = (unsigned)nblk;
+  const dim3 grid((unsigned)nblk, (unsigned)p.nbatch);
+  if (p.nbatch > 65535) return B2_ERR_ARG;
 #define B2_ST_CASE(M)                                                                              \
   case M:                                                                                          \
     stencil_vec_kernel<T, M, ROWS, U, COLS><<<grid, COLS, 0, st>>>((const T*)x, (T*)y, (const T*)lo, \
@@ -282,7 +309,7 @@ int launch_stencil(b2_ctx* ctx, const void* x, void* y, const void* lo, const vo
       default: return launch_vec<T, 4, 4, 128>(x, y, lo, hi, p, mask, st);    // tuned: see profiles/r01_stencil_tuning.md
     }
   } else {
-    size_t total = (size_t)p.nloc * (size_t)p.ncols;
+    size_t total = (size_t)p.nloc * (size_t)p.ncols * (size_t)p.nbatch;
     size_t need = (total + 255) / 256;
     size_t cap = (size_t)ctx->sm_count * 8;
     int grid = (int)(need < cap ? need : cap);
@@ -309,19 +336,21 @@ extern "C" int b2_first_derivative_halo(int kind, int order, int adjoint, int* n
 
 int b2_fd_build_params(StencilParams* p, int n_lo, int n_hi, size_t nrows_local, size_t ncols,
                        size_t row0, size_t nrows_global, int kind, int order, int edge,
-                       double sampling, int adjoint) {
+                       double sampling, int adjoint, int deriv = 1) {
   if (kind != B2_FD_FORWARD && kind != B2_FD_BACKWARD && kind != B2_FD_CENTERED)
     return B2_ERR_UNSUPPORTED;
-  if (kind == B2_FD_CENTERED && order != 3 && order != 5) return B2_ERR_UNSUPPORTED;
+  if (deriv == 1 && kind == B2_FD_CENTERED && order != 3 && order != 5) return B2_ERR_UNSUPPORTED;
   if (row0 + nrows_local > nrows_global) return B2_ERR_ARG;
   const long long N = (long long)nrows_global;
   // interior taps = taps of a row far from both edges of a very long axis
-  row_taps(1000, 2000, kind, order, edge, adjoint, p->interior);
+  row_taps(1000, 2000, deriv, kind, order, edge, adjoint, p->interior);
   for (int s = 0; s < SPECIAL; ++s) {
-    row_taps(s, N, kind, order, edge, adjoint, p->top[s]);
-    row_taps(N - 1 - s, N, kind, order, edge, adjoint, p->bot[s]);
+    row_taps(s, N, deriv, kind, order, edge, adjoint, p->top[s]);
+    row_taps(N - 1 - s, N, deriv, kind, order, edge, adjoint, p->bot[s]);
   }
-  p->scale = 1.0 / sampling;
+  p->scale = (deriv == 2) ? 1.0 / (sampling * sampling) : 1.0 / sampling;
+  p->batch_stride = 0;
+  p->nbatch = 1;
   p->nloc = (long long)nrows_local;
   p->ncols = (long long)ncols;
   p->row0 = (long long)row0;
@@ -359,4 +388,75 @@ extern "C" int b2_first_derivative(b2_ctx* ctx, const void* x, void* y, const vo
     case B2_F64: return launch_stencil<double>(ctx, x, y, halo_lo, halo_hi, p, st);
     default: return B2_ERR_DTYPE;
   }
+}
+
+
+// ---- MPISecondDerivative per-rank apply (basicoperators/SecondDerivative.py:125-257) -----------------
+extern "C" int b2_second_derivative_halo(int kind, int edge, int adjoint, int* need_lo, int* need_hi) {
+  int lo, hi;
+  if (kind == B2_FD_FORWARD) { lo = adjoint ? 2 : 0; hi = adjoint ? 0 : 2; }
+  else if (kind == B2_FD_BACKWARD) { lo = adjoint ? 0 : 2; hi = adjoint ? 2 : 0; }
+  else if (kind == B2_FD_CENTERED) { lo = hi = edge ? 2 : 1; }   // the edge rows reach two rows away
+  else return B2_ERR_UNSUPPORTED;
+  if (need_lo) *need_lo = lo;
+  if (need_hi) *need_hi = hi;
+  return B2_OK;
+}
+
+extern "C" int b2_second_derivative(b2_ctx* ctx, const void* x, void* y, const void* halo_lo, int n_lo,
+                                    const void* halo_hi, int n_hi, size_t nrows_local, size_t ncols, size_t row0,
+                                    size_t nrows_global, int kind, int edge, double sampling, int adjoint,
+                                    int dtype, void* stream) {
+  if (!ctx) return B2_ERR_ARG;
+  if (nrows_local == 0 || ncols == 0) return B2_OK;
+  if (!x || !y) return B2_ERR_ARG;
+  if (n_lo < 0 || n_hi < 0 || n_lo > 8 || n_hi > 8) return B2_ERR_ARG;
+  if (!halo_lo) n_lo = 0;
+  if (!halo_hi) n_hi = 0;
+  int need_lo, need_hi;
+  int rc = b2_second_derivative_halo(kind, edge, adjoint, &need_lo, &need_hi);
+  if (rc) return rc;
+  const long long avail_lo = (long long)row0, avail_hi = (long long)(nrows_global - row0 - nrows_local);
+  // interior rows only need the taps' reach; be strict with the tap reach of this kind
+  int reach_lo = need_lo, reach_hi = need_hi;
+  if (kind == B2_FD_CENTERED) reach_lo = reach_hi = 1;   // 2 only matters next to a global edge (checked by taps)
+  if (n_lo < (reach_lo < avail_lo ? reach_lo : avail_lo)) return B2_ERR_HALO;
+  if (n_hi < (reach_hi < avail_hi ? reach_hi : avail_hi)) return B2_ERR_HALO;
+  StencilParams p;
+  rc = b2_fd_build_params(&p, n_lo, n_hi, nrows_local, ncols, row0, nrows_global, kind, 3, edge, sampling, adjoint, 2);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case B2_F32: return launch_stencil<float>(ctx, x, y, halo_lo, halo_hi, p, st);
+    case B2_F64: return launch_stencil<double>(ctx, x, y, halo_lo, halo_hi, p, st);
+    default: return B2_ERR_DTYPE;
+  }
+}
+
+// ---- rank-local derivative along the MIDDLE axis of a C-ordered [n_outer][n_axis][n_inner] block ------
+// (the non-partitioned directions of MPILaplacian / MPIGradient: Laplacian.py:97-126, Gradient.py:101-119
+//  wrap a serial pylops First/SecondDerivative per rank; here the same stencil kernel runs batched)
+extern "C" int b2_derivative_axis(b2_ctx* ctx, const void* x, void* y, size_t n_outer, size_t n_axis, size_t n_inner,
+                                  int deriv, int kind, int order, int edge, double sampling, int adjoint, int dtype,
+                                  void* stream) {
+  if (!ctx || (deriv != 1 && deriv != 2)) return B2_ERR_ARG;
+  if (n_outer == 0 || n_axis == 0 || n_inner == 0) return B2_OK;
+  if (!x || !y) return B2_ERR_ARG;
+  StencilParams p;
+  int rc = b2_fd_build_params(&p, 0, 0, n_axis, n_inner, 0, n_axis, kind, order, edge, sampling, adjoint, deriv);
+  if (rc) return rc;
+  p.nbatch = 1;
+  p.batch_stride = (long long)(n_axis * n_inner);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (size_t done = 0; done < n_outer; done += 65535) {
+    p.nbatch = (int)(n_outer - done < 65535 ? n_outer - done : 65535);
+    const size_t off = done * n_axis * n_inner * b2_dtype_size(dtype);
+    switch (dtype) {
+      case B2_F32: rc = launch_stencil<float>(ctx, (const char*)x + off, (char*)y + off, nullptr, nullptr, p, st); break;
+      case B2_F64: rc = launch_stencil<double>(ctx, (const char*)x + off, (char*)y + off, nullptr, nullptr, p, st); break;
+      default: return B2_ERR_DTYPE;
+    }
+    if (rc) return rc;
+  }
+  return B2_OK;
 }

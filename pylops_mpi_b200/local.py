@@ -82,3 +82,73 @@ class MatrixMult(LocalOperator):
 
     def rmatvec(self, x, out=None):
         return self._apply(x, _lib.OP_H, out)
+
+
+class _AxisDerivative(LocalOperator):
+    """Rank-local derivative along one axis of a C-ordered ``dims`` block (the role of
+    pylops.FirstDerivative / pylops.SecondDerivative inside MPIBlockDiag in MPILaplacian / MPIGradient,
+    Laplacian.py:97-126, Gradient.py:101-119).  One batched stencil launch (b2_derivative_axis)."""
+    _deriv = 1
+
+    def __init__(self, dims, axis: int = 0, sampling: float = 1.0, kind: str = "centered", edge: bool = False,
+                 order: int = 3, dtype=np.float64):
+        self.dims = tuple(int(d) for d in (dims if np.ndim(dims) else (dims,)))
+        self.axis = axis % len(self.dims)
+        n = int(np.prod(self.dims))
+        self.shape = (n, n)
+        self.sampling, self.edge, self.order = float(sampling), bool(edge), int(order)
+        kinds = {"forward": _lib.FD_FORWARD, "backward": _lib.FD_BACKWARD, "centered": _lib.FD_CENTERED}
+        if kind not in kinds:
+            raise NotImplementedError("'kind' must be 'forward', 'centered', or 'backward'")
+        if self._deriv == 1 and kind == "centered" and order not in (3, 5):
+            raise NotImplementedError("'order' must be '3, or '5'")
+        self._kind = kinds[kind]
+        self._tdtype = _lib.torch_dtype(dtype)
+        self.dtype = _lib.numpy_dtype(self._tdtype)
+        _lib.ctx()
+
+    def _apply(self, x: torch.Tensor, adjoint: int, out=None) -> torch.Tensor:
+        x = x.reshape(-1)
+        if x.dtype != self._tdtype:
+            x = x.to(self._tdtype)
+        if not x.is_contiguous():
+            x = x.contiguous()
+        y = torch.empty_like(x) if out is None else out
+        n_outer = int(np.prod(self.dims[:self.axis])) if self.axis else 1
+        n_axis = self.dims[self.axis]
+        n_inner = int(np.prod(self.dims[self.axis + 1:])) if self.axis + 1 < len(self.dims) else 1
+        cx = self._tdtype.is_complex
+        real = {torch.complex64: torch.float32, torch.complex128: torch.float64}.get(self._tdtype, self._tdtype)
+        if cx and n_inner == 1:
+            # complex along the innermost axis: the (re, im) pairs are the "inner" dimension
+            n_inner = 2
+        elif cx:
+            n_inner *= 2
+        _lib.check(_lib.lib.b2_derivative_axis(_lib.ctx(), x.data_ptr(), y.data_ptr(), n_outer, n_axis, n_inner,
+                                               self._deriv, self._kind, self.order, int(self.edge), self.sampling,
+                                               adjoint, _lib.code(real), _lib.stream()), "b2_derivative_axis")
+        return y
+
+    def _matvec(self, x, out=None):
+        return self._apply(x, 0, out)
+
+    def _rmatvec(self, x, out=None):
+        return self._apply(x, 1, out)
+
+    def matvec(self, x, out=None):
+        return self._apply(x, 0, out)
+
+    def rmatvec(self, x, out=None):
+        return self._apply(x, 1, out)
+
+
+class FirstDerivative(_AxisDerivative):
+    _deriv = 1
+
+
+class SecondDerivative(_AxisDerivative):
+    _deriv = 2
+
+    def __init__(self, dims, axis: int = 0, sampling: float = 1.0, kind: str = "centered", edge: bool = False,
+                 dtype=np.float64):
+        super().__init__(dims, axis=axis, sampling=sampling, kind=kind, edge=edge, order=3, dtype=dtype)

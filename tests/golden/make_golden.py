@@ -42,7 +42,7 @@ def load_reference():
         sys.modules["pylops_mpi." + sub] = m
         setattr(pkg, sub, m)
     mods = {}
-    for name in ("basicoperators.FirstDerivative", "basicoperators.BlockDiag", "basicoperators.VStack",
+    for name in ("basicoperators.FirstDerivative", "basicoperators.SecondDerivative", "basicoperators.BlockDiag", "basicoperators.VStack",
                  "basicoperators.MatrixMult", "signalprocessing.Fredholm1", "optimization.cls_basic",
                  "utils.dottest"):
         mods[name.split(".")[-1]] = importlib.import_module("pylops_mpi." + name)
@@ -55,6 +55,7 @@ def main():
     pkg, mods = load_reference()
     DA, Partition = pkg.DistributedArray, pkg.Partition
     FD = mods["FirstDerivative"].MPIFirstDerivative
+    SD = mods["SecondDerivative"].MPISecondDerivative
     BD = mods["BlockDiag"].MPIBlockDiag
     VS = mods["VStack"].MPIVStack
     MM = mods["MatrixMult"]
@@ -117,6 +118,38 @@ def main():
                         key = f"fd/P{P}/{dims}/h{h}/{kind}{order}/e{int(edge)}/{np.dtype(dtype).name}"
                         try:
                             res = MPI.run_world(P, t_fd, dims, h, kind, edge, order, dtype)
+                        except (ValueError, IndexError) as exc:
+                            put(key + "/reference_raises", type(exc).__name__)
+                            continue
+                        put(key + "/x", res[0]["x"])
+                        for r, d in enumerate(res):
+                            put(key + f"/r{r}/y", d["y_local"])
+                            put(key + f"/r{r}/ya", d["ya_local"])
+                            assert d["dottest"]
+
+    # ---- MPISecondDerivative ("next" row f2) ---------------------------------------------------------------
+    def t_sd(rank, dims, h, kind, edge, dtype):
+        rng = np.random.default_rng(9)
+        n = int(np.prod(dims))
+        x = rng.normal(0, 10, n).astype(dtype)
+        if np.issubdtype(dtype, np.complexfloating):
+            x = x + 1j * rng.normal(0, 10, n)
+        Sop = SD(dims, sampling=h, kind=kind, edge=edge, dtype=dtype)
+        xd = DA.to_dist(x)
+        y = Sop @ xd
+        ya = Sop.H @ xd
+        u = DA.to_dist(rng.normal(0, 10, n).astype(dtype))
+        v = DA.to_dist(rng.normal(0, 10, n).astype(dtype))
+        return {"x": x, "y_local": y.local_array, "ya_local": ya.local_array, "dottest": dottest(Sop, u, v)}
+
+    for P in (1, 2, 3, 4):
+        for dims, h in (((11, 21), 1.0), ((13,), 1.0), ((30, 17), 0.4), ((29, 5, 3), 0.4), ((600,), 1.0)):
+            for kind in ("forward", "backward", "centered"):
+                for edge in (False, True):
+                    for dtype in (np.float64, np.complex128):
+                        key = f"sd/P{P}/{dims}/h{h}/{kind}/e{int(edge)}/{np.dtype(dtype).name}"
+                        try:
+                            res = MPI.run_world(P, t_sd, dims, h, kind, edge, dtype)
                         except (ValueError, IndexError) as exc:
                             put(key + "/reference_raises", type(exc).__name__)
                             continue

@@ -119,6 +119,31 @@ for dims, h in [((600,), 1.0), ((100, 151), 1.0), ((101, 51, 10), 0.4), ((79, 11
                 v = pm.DistributedArray.to_dist(comm.bcast(rng.normal(0, 10, n), 0).astype(dtype))
                 assert pm.dottest(Fop, u, v)
 
+# ---- "next" rows: MPISecondDerivative (per-rank vs oracle) and MPILaplacian (vs dense) --------------------
+for dims, h in [((600,), 1.0), ((100, 37), 0.4), ((41, 9, 6), 0.4)]:
+    for kind in ("forward", "backward", "centered"):
+        for edge in (False, True):
+            n = int(np.prod(dims))
+            xg = comm.bcast(rng.normal(0, 10, n), 0)
+            Sop = pm.MPISecondDerivative(dims, sampling=h, kind=kind, edge=edge)
+            D2 = o.second_derivative_dense(dims[0], h, kind, edge)
+            X = xg.reshape(dims[0], -1)
+            xd = pm.DistributedArray.to_dist(xg)
+            check(f"sd {dims} {kind} {edge}", host((Sop @ xd).asarray()), (D2 @ X).ravel(), 1e-12, 1e-10)
+            check(f"sdH {dims} {kind} {edge}", host((Sop.H @ xd).asarray()), (D2.T @ X).ravel(), 1e-12, 1e-10)
+            try:
+                refl = o.second_derivative(o.to_dist(xg, P), dims, h, kind, edge, False)
+                check("sd per-rank", host((Sop @ xd).local_array), refl[rank], 1e-12, 1e-10)
+            except (ValueError, IndexError):
+                pass
+    if len(dims) > 1:
+        axes = tuple(range(len(dims)))
+        Lop = pm.MPILaplacian(dims, axes=axes, weights=(1.0,) * len(axes), sampling=(1.0, 0.5, 2.0)[:len(axes)], edge=True)
+        xg = comm.bcast(rng.normal(0, 10, int(np.prod(dims))), 0)
+        ref = sum(o.derivative_along_axis(xg.reshape(dims), ax, o.second_derivative_dense(dims[ax], s, "centered", True))
+                  for ax, s in zip(axes, (1.0, 0.5, 2.0)))
+        check(f"laplacian {dims}", host((Lop @ pm.DistributedArray.to_dist(xg)).asarray()), ref.ravel(), 1e-11, 1e-9)
+
 # ---- BlockDiag / VStack / HStack (test_blockdiag.py:24-71, test_stack.py:29-79) ---------------------
 for ny, nx in [(101, 101), (301, 101)]:
     for dtype in (np.float64, np.complex128):

@@ -303,3 +303,89 @@ def test_gpu_fredholm_vs_reference(pm, case):
     y = Fop @ pm.DistributedArray.to_dist(x, partition=pm.Partition.BROADCAST)
     np.testing.assert_allclose(host(y.asarray()), GOLD[case + "/y"], rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(host((Fop.H @ y).asarray()), GOLD[case + "/xa"], rtol=1e-11, atol=1e-11)
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" row f2: MPISecondDerivative -- oracle and CUDA path vs the real reference
+# ---------------------------------------------------------------------------------------------
+SD_CASES = cases("sd", 7)
+
+
+def parse_sd(case):
+    _, P, dims, h, kind, e, dt = case.split("/")
+    return int(P[1:]), ast.literal_eval(dims), float(h[1:]), kind, bool(int(e[1:])), np.dtype(dt)
+
+
+@pytest.mark.parametrize("case", SD_CASES)
+def test_oracle_second_derivative(case):
+    P, dims, h, kind, edge, dt = parse_sd(case)
+    if case + "/reference_raises" in GOLD:
+        with pytest.raises((ValueError, IndexError)):
+            x = np.zeros(int(np.prod(dims)), dtype=dt)
+            o.second_derivative(o.to_dist(x, P), dims, h, kind, edge, False, dtype=dt)
+            o.second_derivative(o.to_dist(x, P), dims, h, kind, edge, True, dtype=dt)
+        return
+    x = GOLD[case + "/x"]
+    y = o.second_derivative(o.to_dist(x, P), dims, h, kind, edge, False, dtype=dt)
+    ya = o.second_derivative(o.to_dist(x, P), dims, h, kind, edge, True, dtype=dt)
+    for r, (gy, gya) in enumerate(zip(ranks_of(case, "y"), ranks_of(case, "ya"))):
+        np.testing.assert_array_equal(y[r], gy.ravel())
+        np.testing.assert_array_equal(ya[r], gya.ravel())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [c for c in SD_CASES if c + "/reference_raises" not in KEYS])
+def test_gpu_second_derivative_vs_reference(pm, case):
+    P, dims, h, kind, edge, dt = parse_sd(case)
+    x = GOLD[case + "/x"]
+    Sop = pm.MPISecondDerivative(dims, sampling=h, kind=kind, edge=edge, dtype=dt)
+    xd = pm.DistributedArray.to_dist(x)
+    gy = np.concatenate([a.ravel() for a in ranks_of(case, "y")])
+    gya = np.concatenate([a.ravel() for a in ranks_of(case, "ya")])
+    np.testing.assert_allclose(host((Sop @ xd).asarray()), gy, rtol=1e-12, atol=1e-11)
+    np.testing.assert_allclose(host((Sop.H @ xd).asarray()), gya, rtol=1e-12, atol=1e-11)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims,axes", [((20, 17), (0, 1)), ((12, 9, 10), (0, 1, 2)), ((12, 9, 10), (-2, -1)), ((31,), (0,))])
+@pytest.mark.parametrize("kind,edge", [("centered", False), ("centered", True), ("forward", False), ("backward", False)])
+@pytest.mark.parametrize("dtype", [np.float64, np.complex128, np.float32])
+def test_gpu_laplacian_and_local_derivatives(pm, dims, axes, kind, edge, dtype):
+    rng = np.random.default_rng(5)
+    n = int(np.prod(dims))
+    x = rng.standard_normal(n).astype(dtype)
+    if np.issubdtype(dtype, np.complexfloating):
+        x = x + 1j * rng.standard_normal(n)
+    weights = tuple(1.0 + 0.5 * i for i in range(len(axes)))
+    sampling = tuple(1.0 + 0.25 * i for i in range(len(axes)))
+    Lop = pm.MPILaplacian(dims, axes=axes, weights=weights, sampling=sampling, kind=kind, edge=edge, dtype=dtype)
+    X = x.reshape(dims)
+    ref = np.zeros(dims, dtype=np.complex128 if np.iscomplexobj(x) else np.float64)
+    refa = np.zeros_like(ref)
+    for ax, w, s in zip(axes, weights, sampling):
+        D = o.second_derivative_dense(dims[ax], s, kind, edge)
+        ref += w * o.derivative_along_axis(X, ax % len(dims), D)
+        refa += w * o.derivative_along_axis(X, ax % len(dims), D.T)
+    tol = dict(rtol=2e-4, atol=2e-4) if dtype == np.float32 else dict(rtol=1e-11, atol=1e-11)
+    xd = pm.DistributedArray.to_dist(x)
+    np.testing.assert_allclose(host((Lop @ xd).asarray()), ref.ravel(), **tol)
+    np.testing.assert_allclose(host((Lop.H @ xd).asarray()), refa.ravel(), **tol)
+    if dtype != np.float32:
+        u = pm.DistributedArray.to_dist(rng.standard_normal(n).astype(dtype))
+        v = pm.DistributedArray.to_dist(rng.standard_normal(n).astype(dtype))
+        assert pm.dottest(Lop, u, v)
+    # rank-local first derivatives along every axis (the MPIGradient building block)
+    for ax in range(len(dims)):
+        for k2, order in (("centered", 3), ("centered", 5), ("forward", 3)):
+            if dims[ax] < 6:
+                continue
+            F = pm.local.FirstDerivative(dims, axis=ax, sampling=0.5, kind=k2, edge=edge, order=order, dtype=dtype)
+            D1 = o.first_derivative_dense(dims[ax], 0.5, k2, edge, order)
+            xt = torch_from(x)
+            np.testing.assert_allclose(host(F.matvec(xt)), o.derivative_along_axis(X, ax, D1).ravel(), **tol)
+            np.testing.assert_allclose(host(F.rmatvec(xt)), o.derivative_along_axis(X, ax, D1.T).ravel(), **tol)
+
+
+def torch_from(a):
+    import torch
+    return torch.as_tensor(a).cuda()
