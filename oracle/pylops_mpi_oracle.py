@@ -865,3 +865,47 @@ def second_derivative_dense(N: int, sampling=1.0, kind="centered", edge=False) -
 def derivative_along_axis(x: np.ndarray, axis: int, D: np.ndarray) -> np.ndarray:
     """apply the dense stencil matrix D along `axis` of x (serial reference for Laplacian terms)"""
     return np.moveaxis(np.tensordot(D, x, axes=([1], [axis])), 0, axis)
+
+
+# --------------------------------------------------------------------------
+# MPIMDC (waveeqprocessing/MDC.py:12-74) -- PARITY UNPINNED: the FFT / Identity stages are third-party
+# pylops operators that are not available here; their convention (orthonormal one-sided FFT with the
+# positive frequencies scaled by sqrt(2), ifftshift of the time axis for two-sided data) is restated
+# from the pylops 2.x documentation.  Used only to check the CUDA pipeline against the same formula.
+# --------------------------------------------------------------------------
+def _fft_real(x, nt, ifftshift_before):
+    if ifftshift_before:
+        x = np.fft.ifftshift(x, axes=0)
+    y = np.fft.rfft(x, n=nt, axis=0, norm="ortho")
+    y[1:1 + (nt - 1) // 2] *= np.sqrt(2)
+    return y
+
+
+def _fft_real_adj(y, nt, ifftshift_before):
+    y = y.copy()
+    y[1:1 + (nt - 1) // 2] /= np.sqrt(2)
+    x = np.fft.irfft(y, n=nt, axis=0, norm="ortho")
+    if ifftshift_before:
+        x = np.fft.fftshift(x, axes=0)
+    return x
+
+
+def mdc(G_loc: List[np.ndarray], x: np.ndarray, nt: int, nv: int, twosided=True, adjoint=False,
+        dt=1.0, dr=1.0, prescaled=False) -> np.ndarray:
+    """d = F1^H I1^H Fredholm1 I F m  (MDC.py:55-69) with G split over ranks along frequency."""
+    nfmax = sum(g.shape[0] for g in G_loc)
+    ns, nr = G_loc[0].shape[1:]
+    nfft = int(np.ceil((nt + 1) / 2))
+    sc = 1.0 if prescaled else dr * dt * np.sqrt(nt)
+    Gs = [sc * g for g in G_loc]
+    if not adjoint:
+        X = _fft_real(np.real(x).reshape(nt, nr, nv), nt, twosided)[:nfmax]
+        Y = fredholm1(Gs, X.ravel(), nv).reshape(nfmax, ns, nv)
+        Yp = np.zeros((nfft, ns, nv), dtype=Y.dtype)
+        Yp[:nfmax] = Y
+        return _fft_real_adj(Yp, nt, False).ravel()
+    Y = _fft_real(np.real(x).reshape(nt, ns, nv), nt, False)[:nfmax]
+    X = fredholm1(Gs, Y.ravel(), nv, adjoint=True).reshape(nfmax, nr, nv)
+    Xp = np.zeros((nfft, nr, nv), dtype=X.dtype)
+    Xp[:nfmax] = X
+    return _fft_real_adj(Xp, nt, twosided).ravel()

@@ -341,3 +341,34 @@ def test_matrixmult_bf16(pm, kind, M):
     refa = A64.T @ yb
     erra = np.abs(host(ya.asarray()).reshape(K, M) - refa)
     assert np.all(erra <= (np.abs(A64.T) @ np.abs(yb)) * N * 6e-8 + 1e-6)
+
+
+# ---- MPIMDC ("next" row f1; parity UNPINNED: checked against the oracle's restatement + dottest) ------
+@pytest.mark.parametrize("twosided", [True, False])
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_mdc_pipeline(pm, twosided, dtype):
+    rng = np.random.default_rng(11)
+    ns, nr, nv, nt = 6, 5, 3, 31 if twosided else 32
+    nfft = int(np.ceil((nt + 1) / 2))
+    nfmax = nfft - 3
+    G = (rng.standard_normal((nfmax, ns, nr)) + 1j * rng.standard_normal((nfmax, ns, nr))).astype(dtype)
+    rdt = np.float32 if dtype == np.complex64 else np.float64
+    Mop = pm.MPIMDC(G, nt=nt, nv=nv, nfreq=nfmax, dt=0.004, dr=2.0, twosided=twosided)
+    assert Mop.shape == (nt * ns * nv, nt * nr * nv)
+    m = rng.standard_normal(nt * nr * nv).astype(rdt)
+    md = pm.DistributedArray.to_dist(m, partition=pm.Partition.BROADCAST)
+    d = Mop @ md
+    assert d.partition is pm.Partition.BROADCAST
+    ref = o.mdc([G.astype(np.complex128)], m.astype(np.float64), nt, nv, twosided, False, dt=0.004, dr=2.0)
+    tol = 2e-4 if dtype == np.complex64 else 1e-11
+    np.testing.assert_allclose(host(d.asarray()).real, ref, rtol=tol, atol=tol * np.abs(ref).max())
+    dd = rng.standard_normal(nt * ns * nv).astype(rdt)
+    ma = Mop.H @ pm.DistributedArray.to_dist(dd, partition=pm.Partition.BROADCAST)
+    refa = o.mdc([G.astype(np.complex128)], dd.astype(np.float64), nt, nv, twosided, True, dt=0.004, dr=2.0)
+    np.testing.assert_allclose(host(ma.asarray()).real, refa, rtol=tol, atol=tol * np.abs(refa).max())
+    # adjointness of the whole chain on real vectors
+    lhs = float(np.dot(host(d.asarray()).real.astype(np.float64), dd.astype(np.float64)))
+    rhs = float(np.dot(m.astype(np.float64), host(ma.asarray()).real.astype(np.float64)))
+    assert abs(lhs - rhs) <= (1e-3 if dtype == np.complex64 else 1e-10) * max(abs(lhs), abs(rhs), 1.0)
+    with pytest.raises(ValueError):
+        pm.MPIMDC(G, nt=30, nv=nv, nfreq=nfmax, twosided=True)
