@@ -13,6 +13,7 @@ from .basicoperators import *  # noqa: F401,F403
 from .signalprocessing import *  # noqa: F401,F403
 from . import waveeqprocessing  # noqa: F401
 from .waveeqprocessing import MPIMDC  # noqa: F401
+from .StackedArray import StackedDistributedArray, MPIStackedVStack, MPIGradient  # noqa: F401
 from .optimization.basic import cg, cgls  # noqa: F401
 from .optimization.cls_basic import CG, CGLS  # noqa: F401
 from .utils.dottest import dottest  # noqa: F401

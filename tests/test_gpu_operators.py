@@ -372,3 +372,30 @@ def test_mdc_pipeline(pm, twosided, dtype):
     assert abs(lhs - rhs) <= (1e-3 if dtype == np.complex64 else 1e-10) * max(abs(lhs), abs(rhs), 1.0)
     with pytest.raises(ValueError):
         pm.MPIMDC(G, nt=30, nv=nv, nfreq=nfmax, twosided=True)
+
+
+# ---- MPIGradient / stacked glue ("next" row f3, minimal) --------------------------------------------------
+@pytest.mark.parametrize("dims", [(20, 17), (12, 9, 10)])
+@pytest.mark.parametrize("kind,edge", [("centered", True), ("forward", False)])
+def test_gradient_stacked(pm, dims, kind, edge):
+    rng = np.random.default_rng(2)
+    n = int(np.prod(dims))
+    x = rng.standard_normal(n)
+    samp = tuple(1.0 + 0.5 * i for i in range(len(dims)))
+    Gop = pm.MPIGradient(dims, sampling=samp, edge=edge, kind=kind, dtype=np.float64)
+    y = Gop.matvec(pm.DistributedArray.to_dist(x))
+    assert isinstance(y, pm.StackedDistributedArray) and y.narrays == len(dims)
+    X = x.reshape(dims)
+    refs = [o.derivative_along_axis(X, ax, o.first_derivative_dense(dims[ax], samp[ax], kind, edge, 3)).ravel()
+            for ax in range(len(dims))]
+    for ax in range(len(dims)):
+        np.testing.assert_allclose(host(y[ax].asarray()), refs[ax], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(host(y.asarray()), np.concatenate(refs), rtol=1e-12, atol=1e-12)
+    xa = Gop.rmatvec(y)
+    refa = sum(o.derivative_along_axis(refs[ax].reshape(dims), ax, o.first_derivative_dense(dims[ax], samp[ax], kind, edge, 3).T)
+               for ax in range(len(dims)))
+    np.testing.assert_allclose(host(xa.asarray()), refa.ravel(), rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(y.dot(y)[0], sum(np.dot(r, r) for r in refs), rtol=1e-12)
+    np.testing.assert_allclose(y.norm()[0], np.sqrt(sum(np.dot(r, r) for r in refs)), rtol=1e-12)
+    z = y + y * 2.0 - y
+    np.testing.assert_allclose(host(z.asarray()), 2 * np.concatenate(refs), rtol=1e-12, atol=1e-12)
