@@ -909,3 +909,53 @@ def mdc(G_loc: List[np.ndarray], x: np.ndarray, nt: int, nv: int, twosided=True,
     Xp = np.zeros((nfft, nr, nv), dtype=X.dtype)
     Xp[:nfmax] = X
     return _fft_real_adj(Xp, nt, twosided).ravel()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# "next" rows f2/f3: MPIGradient (basicoperators/Gradient.py:88-119) and MPILaplacian
+# (basicoperators/Laplacian.py:97-127) -- axis 0 is the distributed stencil above, the other axes are
+# rank-local stencils (third-party pylops.FirstDerivative / SecondDerivative, restated as the dense
+# operators of first_derivative_dense / second_derivative_dense applied along the axis of the rank's block).
+# Pinned against the reference's own glue run over refshim/pylops/_derivatives.py (tests/golden).
+# ---------------------------------------------------------------------------------------------------------
+def _local_axis(x_flat, dims, axis, D_of_n, adjoint):
+    """rank-local operator inside MPIBlockDiag: @reshaped(stacking=True) first re-partitions the flat
+    vector to the operator's row blocks (BlockDiag.py:121-131, utils/decorators.py:70-85)"""
+    shapes = local_shapes(tuple(dims), len(x_flat), SCATTER, 0)
+    out = []
+    for xl, shp in zip(reshaped_in(x_flat, shapes), shapes):
+        D = D_of_n(shp[axis])
+        out.append(derivative_along_axis(np.asarray(xl).reshape(shp), axis, D.T if adjoint else D).ravel())
+    return out
+
+
+def gradient(x_flat: List[np.ndarray], dims, sampling, kind="centered", edge=False) -> List[List[np.ndarray]]:
+    """forward MPIGradient: list (one entry per axis) of per-rank flat arrays (Gradient.py:101-119)"""
+    out = [first_derivative(x_flat, tuple(dims), sampling[0], kind, edge, 3, False)]
+    for ax in range(1, len(dims)):
+        out.append(_local_axis(x_flat, dims, ax, lambda n: first_derivative_dense(n, sampling[ax], kind, edge, 3), False))
+    return out
+
+
+def gradient_adjoint(y_flat: List[List[np.ndarray]], dims, sampling, kind="centered", edge=False) -> List[np.ndarray]:
+    """adjoint MPIGradient: sum over axes of the per-axis adjoints (VStack.py:195-201)"""
+    acc = first_derivative(y_flat[0], tuple(dims), sampling[0], kind, edge, 3, True)
+    for ax in range(1, len(dims)):
+        part = _local_axis(y_flat[ax], dims, ax, lambda n: first_derivative_dense(n, sampling[ax], kind, edge, 3), True)
+        acc = [a + p for a, p in zip(acc, part)]
+    return acc
+
+
+def laplacian(x_flat: List[np.ndarray], dims, axes, weights, sampling, kind="centered", edge=False,
+              adjoint=False) -> List[np.ndarray]:
+    """MPILaplacian: weighted sum of second derivatives (Laplacian.py:97-127)"""
+    acc = None
+    for ax, w, s in zip(axes, weights, sampling):
+        ax = ax % len(dims)
+        if ax == 0:
+            part = second_derivative(x_flat, tuple(dims), s, kind, edge, adjoint)
+        else:
+            part = _local_axis(x_flat, dims, ax, lambda n: second_derivative_dense(n, s, kind, edge), adjoint)
+        part = [w * p for p in part]
+        acc = part if acc is None else [a + p for a, p in zip(acc, part)]
+    return acc

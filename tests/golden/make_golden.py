@@ -46,6 +46,10 @@ def load_reference():
                  "basicoperators.MatrixMult", "signalprocessing.Fredholm1", "optimization.cls_basic",
                  "utils.dottest"):
         mods[name.split(".")[-1]] = importlib.import_module("pylops_mpi." + name)
+    bo = sys.modules["pylops_mpi.basicoperators"]
+    bo.MPIBlockDiag, bo.MPISecondDerivative = mods["BlockDiag"].MPIBlockDiag, mods["SecondDerivative"].MPISecondDerivative
+    for name in ("basicoperators.Gradient", "basicoperators.Laplacian"):  # "next" rows: the reference's own glue over
+        mods[name.split(".")[-1]] = importlib.import_module("pylops_mpi." + name)  # refshim/pylops/_derivatives.py
     return pkg, mods
 
 
@@ -270,7 +274,43 @@ def main():
                     for k, v in res.items():
                         put(f"fredholm/P{P}/nz{nz}/{np.dtype(dtype).name}/s{int(saveGt)}m{int(usematmul)}/{k}", v)
 
-    path = os.path.join(HERE, "reference_golden.npz")
+    # ---- MPIGradient / MPILaplacian ("next" rows f2/f3; rank-local stencils restated in refshim/pylops) -------
+    GR, LP = mods["Gradient"].MPIGradient, mods["Laplacian"].MPILaplacian
+
+    def t_grad(rank, dims, samp, kind, edge, dtype):
+        rng = np.random.default_rng(13)
+        n = int(np.prod(dims))
+        x = rng.normal(0, 10, n).astype(dtype)
+        Gop = GR(dims, sampling=samp, kind=kind, edge=edge, dtype=dtype)
+        y = Gop.matvec(DA.to_dist(x))
+        xa = Gop.rmatvec(y)
+        res = {"x": x, "xa": xa.local_array, "dot": y.dot(y), "norm": y.norm()}
+        for i in range(y.narrays):
+            res[f"y{i}"] = y[i].local_array
+        return res
+
+    def t_lap(rank, dims, axes, weights, samp, kind, edge, dtype):
+        rng = np.random.default_rng(14)
+        n = int(np.prod(dims))
+        x = rng.normal(0, 10, n).astype(dtype)
+        Lop = LP(dims, axes=axes, weights=weights, sampling=samp, kind=kind, edge=edge, dtype=dtype)
+        xd = DA.to_dist(x)
+        return {"x": x, "y": (Lop @ xd).local_array, "ya": (Lop.H @ xd).local_array}
+
+    for P in (1, 2, 3):
+        for dims, samp in (((21, 11), (1.0, 0.5)), ((13, 6, 7), (0.4, 1.0, 2.0))):
+            for kind, edge in (("centered", True), ("centered", False), ("forward", False), ("backward", True)):
+                for r, d in enumerate(MPI.run_world(P, t_grad, dims, samp, kind, edge, np.float64)):
+                    for k, v in d.items():
+                        put(f"grad/P{P}/{dims}/{kind}/e{int(edge)}/r{r}/{k}", v)
+        for dims, axes, weights, samp in (((21, 11), (-2, -1), (1, 1), (1, 1)), ((21, 11), (0, 1), (2.0, 0.5), (0.4, 1.5)),
+                                          ((13, 6, 7), (1, 2), (1, -2), (1.0, 0.5)), ((13, 6, 7), (2, 0), (1.5, 1), (1.0, 0.5))):
+            for kind, edge in (("centered", True), ("forward", False), ("backward", False)):
+                for r, d in enumerate(MPI.run_world(P, t_lap, dims, axes, weights, samp, kind, edge, np.float64)):
+                    for k, v in d.items():
+                        put(f"lap/P{P}/{dims}/{axes}/{weights}/{samp}/{kind}/e{int(edge)}/r{r}/{k}", v)
+
+    path = os.path.join(HERE, os.environ.get("GOLDEN_OUT", "reference_golden.npz"))
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1e6:.2f} MB")
 

@@ -30,3 +30,5 @@ class MatrixMult(LinearOperator):
 
 
 from . import utils, optimization  # noqa: E402,F401
+from ._derivatives import FirstDerivative, SecondDerivative  # noqa: E402,F401
+from . import basicoperators  # noqa: E402,F401

@@ -1,8 +1,9 @@
-from numbers import Integral
-import numpy as np
+from collections.abc import Sized
 
 
 def _value_or_sized_to_tuple(value, repeat=1):
-    if isinstance(value, (Integral, np.integer)):
-        return tuple([int(value)] * repeat)
-    return tuple(int(v) for v in value)
+    if isinstance(value, tuple):
+        return value
+    if not isinstance(value, Sized):
+        return tuple([value] * repeat)
+    return tuple(value)

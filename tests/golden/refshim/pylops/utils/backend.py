@@ -16,3 +16,8 @@ def get_module_name(mod):
 
 def to_numpy(x):
     return x
+
+
+def get_normalize_axis_index():
+    from numpy.lib.array_utils import normalize_axis_index
+    return normalize_axis_index

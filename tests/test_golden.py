@@ -389,3 +389,84 @@ def test_gpu_laplacian_and_local_derivatives(pm, dims, axes, kind, edge, dtype):
 def torch_from(a):
     import torch
     return torch.as_tensor(a).cuda()
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" rows: MPIGradient / MPILaplacian -- the reference's glue (StackedDistributedArray, MPIStackedVStack,
+# MPIBlockDiag re-partition, operator algebra) run over refshim's restated rank-local stencils
+# ---------------------------------------------------------------------------------------------
+GRAD_CASES = cases("grad", 5)
+LAP_CASES = cases("lap", 8)
+
+
+def parse_grad(case):
+    _, P, dims, kind, e = case.split("/")
+    dims = ast.literal_eval(dims)
+    samp = {2: (1.0, 0.5), 3: (0.4, 1.0, 2.0)}[len(dims)]
+    return int(P[1:]), dims, samp, kind, bool(int(e[1:]))
+
+
+def parse_lap(case):
+    _, P, dims, axes, weights, samp, kind, e = case.split("/")
+    return (int(P[1:]), ast.literal_eval(dims), ast.literal_eval(axes), ast.literal_eval(weights),
+            ast.literal_eval(samp), kind, bool(int(e[1:])))
+
+
+def test_next_fixture_inventory():
+    assert len(GRAD_CASES) == 3 * 2 * 4 and len(LAP_CASES) == 3 * 4 * 3
+
+
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_oracle_gradient(case):
+    P, dims, samp, kind, edge = parse_grad(case)
+    x = GOLD[case + "/r0/x"]
+    y = o.gradient(o.to_dist(x, P), dims, samp, kind, edge)
+    for ax in range(len(dims)):
+        for r, g in enumerate(ranks_of(case, f"y{ax}")):
+            np.testing.assert_allclose(y[ax][r], g.ravel(), rtol=1e-13, atol=1e-12)
+    xa = o.gradient_adjoint(y, dims, samp, kind, edge)
+    for r, g in enumerate(ranks_of(case, "xa")):
+        np.testing.assert_allclose(xa[r], g.ravel(), rtol=1e-13, atol=1e-11)
+    flat = np.concatenate([np.concatenate(a) for a in y])
+    np.testing.assert_allclose(np.dot(flat, flat), GOLD[case + "/r0/dot"], rtol=1e-13)
+    np.testing.assert_allclose(np.linalg.norm(flat), GOLD[case + "/r0/norm"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("case", LAP_CASES)
+def test_oracle_laplacian(case):
+    P, dims, axes, weights, samp, kind, edge = parse_lap(case)
+    x = GOLD[case + "/r0/x"]
+    y = o.laplacian(o.to_dist(x, P), dims, axes, weights, samp, kind, edge, False)
+    ya = o.laplacian(o.to_dist(x, P), dims, axes, weights, samp, kind, edge, True)
+    for r, (g, ga) in enumerate(zip(ranks_of(case, "y"), ranks_of(case, "ya"))):
+        np.testing.assert_allclose(y[r], g.ravel(), rtol=1e-13, atol=1e-11)
+        np.testing.assert_allclose(ya[r], ga.ravel(), rtol=1e-13, atol=1e-11)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", GRAD_CASES)
+def test_gpu_gradient_vs_reference(pm, case):
+    P, dims, samp, kind, edge = parse_grad(case)
+    x = GOLD[case + "/r0/x"]
+    Gop = pm.MPIGradient(dims, sampling=samp, kind=kind, edge=edge, dtype=np.float64)
+    y = Gop.matvec(pm.DistributedArray.to_dist(x))
+    for ax in range(len(dims)):
+        g = np.concatenate([a.ravel() for a in ranks_of(case, f"y{ax}")])
+        np.testing.assert_allclose(host(y[ax].asarray()), g, rtol=1e-12, atol=1e-11)
+    ga = np.concatenate([a.ravel() for a in ranks_of(case, "xa")])
+    np.testing.assert_allclose(host(Gop.rmatvec(y).asarray()), ga, rtol=1e-12, atol=1e-10)
+    np.testing.assert_allclose(y.dot(y), GOLD[case + "/r0/dot"], rtol=1e-12)
+    np.testing.assert_allclose(y.norm(), GOLD[case + "/r0/norm"], rtol=1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", LAP_CASES)
+def test_gpu_laplacian_vs_reference(pm, case):
+    P, dims, axes, weights, samp, kind, edge = parse_lap(case)
+    x = GOLD[case + "/r0/x"]
+    Lop = pm.MPILaplacian(dims, axes=axes, weights=weights, sampling=samp, kind=kind, edge=edge, dtype=np.float64)
+    xd = pm.DistributedArray.to_dist(x)
+    g = np.concatenate([a.ravel() for a in ranks_of(case, "y")])
+    ga = np.concatenate([a.ravel() for a in ranks_of(case, "ya")])
+    np.testing.assert_allclose(host((Lop @ xd).asarray()), g, rtol=1e-12, atol=1e-10)
+    np.testing.assert_allclose(host((Lop.H @ xd).asarray()), ga, rtol=1e-12, atol=1e-10)
