@@ -404,6 +404,16 @@ def run_extras(pm, L, comm, peaks, args):
     out["dot_f32_2^28_per_gpu"] = {"GB/s": gbs(8 * n * size, ms), "frac_hbm": gbs(8 * n, ms) / hbm, "us": ms / K * 1e3}
     ms = time_loop(lambda: a._norm_device(2), K, W, comm)
     out["norm2_f32_2^28_per_gpu"] = {"GB/s": gbs(4 * n * size, ms), "frac_hbm": gbs(4 * n, ms) / hbm, "us": ms / K * 1e3}
+    # --- "next" row: fused ISTA / FISTA model update (ISTA: 2 reads + 1 write, FISTA: 3 reads + 2 writes per elem) ---
+    from pylops_mpi_b200.optimization.cls_sparsity import _sparse_update
+    sums = torch.zeros(4, dtype=torch.float64, device="cuda")
+    xa, ga = a.local_array, b.local_array
+    ms = time_loop(lambda: _sparse_update(xa, ga, 1e-3, xa, 1e-4, L.THRESH_SOFT, xa, None, 0.0, sums), K, W)
+    out["ista_update_f32_2^28"] = {"GB/s": gbs(12 * n, ms), "frac_hbm": gbs(12 * n, ms) / hbm, "us": ms / K * 1e3}
+    za = torch.randn_like(xa)
+    ms = time_loop(lambda: _sparse_update(za, ga, 1e-3, xa, 1e-4, L.THRESH_SOFT, xa, za, 0.3, sums), K, W)
+    out["fista_update_f32_2^28"] = {"GB/s": gbs(20 * n, ms), "frac_hbm": gbs(20 * n, ms) / hbm, "us": ms / K * 1e3}
+    del za
     small = pm.DistributedArray(global_shape=10000 * size, dtype=np.float32)
     small.local_array.normal_()
     ms = time_loop(lambda: small.dot(small), 50, 5, comm)

@@ -35,6 +35,7 @@ enum { B2_NRM_COUNT_NONZERO = 0, B2_NRM_SUM_ABS = 1, B2_NRM_SUM_SQ = 2,
 enum { B2_FD_FORWARD = 0, B2_FD_BACKWARD = 1, B2_FD_CENTERED = 2 };
 /* op(A) for gemv/gemm */
 enum { B2_OP_N = 0, B2_OP_T = 1, B2_OP_H = 2 };
+enum { B2_THRESH_NONE = 0, B2_THRESH_SOFT = 1, B2_THRESH_HARD = 2, B2_THRESH_HALF = 3 };
 
 /* error codes >= 2000 are library-level */
 enum { B2_OK = 0, B2_ERR_DTYPE = 2001, B2_ERR_ARG = 2002, B2_ERR_HALO = 2003,
@@ -89,6 +90,15 @@ int b2_dot_multi(b2_ctx* ctx, int k, const void* const* xs, const void* const* y
  * a = kold / (q.q + damp c.c) and ratio b = k / kold (cls_basic.py:389, 395) with no host sync */
 int b2_scalar_div(double* out_dev, const double* num_dev, const double* den1_dev,
                   const double* den2_dev, double alpha, void* stream);
+
+/* ---- ISTA / FISTA model update ("next" row; optimization/cls_sparsity.py:270-343, 578-662) in ONE pass:
+ *   u = base + alpha*g (g may be NULL);  v = threshold_kind(u, thresh) (_apply_thresh, cls_sparsity.py:21-46);
+ *   xnew = v;  znew = v + c*(v - xold) (znew may be NULL; FISTA's auxiliary model, :640-644);
+ *   sums_dev[0] = sum|v - xold|^2 (0 if xold NULL), sums_dev[1] = sum|v| -- local partials of the update norm
+ *   (:331) and the l1 cost (:333).  xnew/znew may alias base/xold.  HALF is real-only. */
+int b2_sparse_update(b2_ctx* ctx, const void* base, const void* g, double alpha, const void* xold,
+                     double thresh, int kind, void* xnew, void* znew, double c, double* sums_dev,
+                     size_t n, int dtype, void* stream);
 
 /* ---- MPIFirstDerivative per-rank apply (FirstDerivative.py:129-319) -------
  * x,y: this rank's row block [nrows_local x ncols] (C order) of the global

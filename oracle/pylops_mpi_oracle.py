@@ -959,3 +959,66 @@ def laplacian(x_flat: List[np.ndarray], dims, axes, weights, sampling, kind="cen
         part = [w * p for p in part]
         acc = part if acc is None else [a + p for a, p in zip(acc, part)]
     return acc
+
+
+# ---------------------------------------------------------------------------------------------------------
+# "next" row: ISTA / FISTA (optimization/cls_sparsity.py:140-343, 578-715) on a dense global operator.  The
+# recurrences involve only global vectors and global norms, so the P-rank run equals the 1-rank run up to the
+# reduction order.  Thresholds: third-party pylops.optimization.cls_sparsity (published formulas).  Pinned
+# against the reference's own loops run over refshim (tests/golden, key "sparse/").
+# ---------------------------------------------------------------------------------------------------------
+def threshold(x: np.ndarray, thresh: float, kind: str) -> np.ndarray:
+    a = np.abs(x)
+    if kind == "soft":
+        if np.iscomplexobj(x):
+            return np.maximum(a - thresh, 0.0) * np.exp(1j * np.angle(x))
+        return np.maximum(a - thresh, 0.0) * np.sign(x)
+    if kind == "hard":
+        return np.where(a <= np.sqrt(2 * thresh), 0, x)
+    if kind == "half":
+        arg = np.ones_like(x)
+        nz = x != 0
+        arg[nz] = (thresh / 8.0) * (a[nz] / 3.0) ** (-1.5)
+        phi = 2.0 / 3.0 * np.arccos(np.clip(arg, -1, 1))
+        x1 = 2.0 / 3.0 * x * (1 + np.cos(2.0 * np.pi / 3.0 - phi))
+        return np.where(a <= (54 ** (1.0 / 3.0) / 4.0) * thresh ** (2.0 / 3.0), 0, x1)
+    raise ValueError(f"threshkind must be hard, soft, half, got {kind}")
+
+
+def ista(A: np.ndarray, y: np.ndarray, x0: np.ndarray, niter: int, eps: float, alpha: float, tol: float = 1e-10,
+         threshkind: str = "soft", fista: bool = False):
+    """returns (x, iiter, cost); ``fista=True`` adds the momentum of cls_sparsity.py:636-644"""
+    thresh = eps * alpha * 0.5                                            # :246
+    x = x0.copy()
+    z = x.copy()
+    t = 1.0
+    cost, iiter, xupdate = [], 0, np.inf
+    while iiter < niter and xupdate > tol:                                # :376 / :693
+        xold = x.copy()
+        res = y - A @ (z if fista else x)
+        x = threshold((z if fista else x) + alpha * (A.conj().T @ res), thresh, threshkind)
+        if fista:
+            told = t
+            t = (1.0 + np.sqrt(1.0 + 4.0 * t ** 2)) / 2.0
+            z = x + ((told - 1.0) / t) * (x - xold)
+            res = y - A @ x                                               # :652 cost on the new x
+        xupdate = np.linalg.norm(x - xold)
+        cost.append(0.5 * np.linalg.norm(res) ** 2 + eps * np.sum(np.abs(x)))
+        iiter += 1
+    return x, iiter, np.array(cost)
+
+
+def power_iteration(A: np.ndarray, niter: int = 10, tol: float = 1e-5, seed: int = 0):
+    """optimization/eigs.py:10-98 (start vector differs: the reference draws it from the global NumPy RNG)"""
+    rng = np.random.default_rng(seed)
+    b = rng.random(A.shape[1]).astype(A.dtype)
+    b /= np.linalg.norm(b)
+    old = 0.0
+    for it in range(niter):
+        b1 = A @ b
+        eig = np.vdot(b, b1)
+        b = b1 / np.linalg.norm(b1)
+        if np.abs(eig - old) < tol * eig:
+            break
+        old = eig
+    return eig, b, it + 1

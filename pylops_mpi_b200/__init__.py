@@ -16,6 +16,9 @@ from .waveeqprocessing import MPIMDC  # noqa: F401
 from .StackedArray import StackedDistributedArray, MPIStackedVStack, MPIGradient  # noqa: F401
 from .optimization.basic import cg, cgls  # noqa: F401
 from .optimization.cls_basic import CG, CGLS  # noqa: F401
+from .optimization.sparsity import ista, fista  # noqa: F401
+from .optimization.cls_sparsity import ISTA, FISTA  # noqa: F401
+from .optimization.eigs import power_iteration  # noqa: F401
 from .utils.dottest import dottest  # noqa: F401
 from . import local  # noqa: F401
 from .local import MatrixMult  # noqa: F401

@@ -21,6 +21,7 @@ SUM, MAX, MIN = 0, 1, 2
 NRM_COUNT_NONZERO, NRM_SUM_ABS, NRM_SUM_SQ, NRM_MAX_ABS, NRM_MIN_ABS, NRM_SUM_POW = range(6)
 FD_FORWARD, FD_BACKWARD, FD_CENTERED = 0, 1, 2
 OP_N, OP_T, OP_H = 0, 1, 2
+THRESH_NONE, THRESH_SOFT, THRESH_HARD, THRESH_HALF = 0, 1, 2, 3
 
 _TORCH2CODE = {torch.float32: F32, torch.float64: F64, torch.complex64: C64,
                torch.complex128: C128, torch.bfloat16: BF16, torch.int64: I64}
@@ -76,6 +77,7 @@ def _load():
         "b2_norm_partial": ([vp, vp, sz, i, i, d, vp, vp], i),
         "b2_dot_multi": ([vp, i, C.POINTER(vp), C.POINTER(vp), sz, i, i, vp, vp], i),
         "b2_scalar_div": ([vp, vp, vp, vp, d, vp], i),
+        "b2_sparse_update": ([vp, vp, vp, d, vp, d, i, vp, vp, d, vp, sz, i, vp], i),
         "b2_first_derivative": ([vp, vp, vp, vp, i, vp, i, sz, sz, sz, sz, i, i, i, d, i, i, vp], i),
         "b2_first_derivative_halo": ([i, i, i, C.POINTER(i), C.POINTER(i)], i),
         "b2_second_derivative": ([vp, vp, vp, vp, i, vp, i, sz, sz, sz, sz, i, i, d, i, i, vp], i),

@@ -48,7 +48,7 @@ def load_reference():
         mods[name.split(".")[-1]] = importlib.import_module("pylops_mpi." + name)
     bo = sys.modules["pylops_mpi.basicoperators"]
     bo.MPIBlockDiag, bo.MPISecondDerivative = mods["BlockDiag"].MPIBlockDiag, mods["SecondDerivative"].MPISecondDerivative
-    for name in ("basicoperators.Gradient", "basicoperators.Laplacian"):  # "next" rows: the reference's own glue over
+    for name in ("basicoperators.Gradient", "basicoperators.Laplacian", "optimization.eigs", "optimization.cls_sparsity"):  # "next" rows: the reference's own glue over
         mods[name.split(".")[-1]] = importlib.import_module("pylops_mpi." + name)  # refshim/pylops/_derivatives.py
     return pkg, mods
 
@@ -309,6 +309,41 @@ def main():
                 for r, d in enumerate(MPI.run_world(P, t_lap, dims, axes, weights, samp, kind, edge, np.float64)):
                     for k, v in d.items():
                         put(f"lap/P{P}/{dims}/{axes}/{weights}/{samp}/{kind}/e{int(edge)}/r{r}/{k}", v)
+
+    # ---- ISTA / FISTA ("next" row: sparsity solvers; thresholds restated in refshim/pylops) ------------------
+    ISTA, FISTA = mods["cls_sparsity"].ISTA, mods["cls_sparsity"].FISTA
+    power_iteration = mods["eigs"].power_iteration
+
+    def t_sparse(rank, P, solver, threshkind, dtype, niter, eps):
+        rng = np.random.default_rng(21)
+        ny, nx = 13, 11
+        blocks = []
+        for r in range(P):
+            A = rng.standard_normal((ny, nx))
+            if np.issubdtype(dtype, np.complexfloating):
+                A = A + 1j * rng.standard_normal((ny, nx))
+            blocks.append(A.astype(dtype))
+        xtrue = np.zeros(P * nx, dtype=dtype)
+        xtrue[rng.permutation(P * nx)[:max(2, P * nx // 5)]] = rng.standard_normal(max(2, P * nx // 5)) * 3
+        Op = BD([pylops.MatrixMult(blocks[rank], dtype=dtype)])
+        xt = DA.to_dist(xtrue)
+        y = Op @ xt
+        x0 = DA(global_shape=P * nx, dtype=dtype)
+        x0[:] = 0
+        lam = max(np.linalg.norm(b, 2) ** 2 for b in blocks)
+        S = (ISTA if solver == "ista" else FISTA)(Op)
+        x, iiter, cost = S.solve(y, x0, niter=niter, eps=eps, alpha=1.0 / lam, tol=1e-10, threshkind=threshkind)
+        eig = power_iteration(Op.H @ Op, niter=200, tol=1e-12, dtype=dtype, backend="numpy",
+                              b_k=DA(global_shape=P * nx, dtype=dtype))[0]
+        return {"x": x.asarray(), "iiter": iiter, "cost": cost, "maxeig": np.abs(eig), "lam": lam}
+
+    for P in (1, 2, 3):
+        for solver in ("ista", "fista"):
+            for threshkind, dtype, eps in (("soft", np.float64, 0.5), ("hard", np.float64, 0.05), ("half", np.float64, 0.2),
+                                           ("soft", np.complex128, 0.5), ("soft", np.float32, 0.5)):
+                res = MPI.run_world(P, t_sparse, P, solver, threshkind, dtype, 40, eps)[0]
+                for k, v in res.items():
+                    put(f"sparse/P{P}/{solver}/{threshkind}/{np.dtype(dtype).name}/{k}", v)
 
     path = os.path.join(HERE, os.environ.get("GOLDEN_OUT", "reference_golden.npz"))
     np.savez_compressed(path, **out)

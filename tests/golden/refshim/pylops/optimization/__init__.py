@@ -1,1 +1,1 @@
-from . import basesolver  # noqa: F401
+from . import basesolver, cls_sparsity  # noqa: F401

@@ -470,3 +470,77 @@ def test_gpu_laplacian_vs_reference(pm, case):
     ga = np.concatenate([a.ravel() for a in ranks_of(case, "ya")])
     np.testing.assert_allclose(host((Lop @ xd).asarray()), g, rtol=1e-12, atol=1e-10)
     np.testing.assert_allclose(host((Lop.H @ xd).asarray()), ga, rtol=1e-12, atol=1e-10)
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" row: ISTA / FISTA -- the reference's solver loops (cls_sparsity.py) over refshim's restated thresholds
+# ---------------------------------------------------------------------------------------------
+SPARSE_CASES = cases("sparse", 5)
+
+
+def sparse_inputs(case):
+    """same construction as make_golden.t_sparse"""
+    _, P, solver, kind, dt = case.split("/")
+    P, dtype = int(P[1:]), np.dtype(dt).type
+    eps = {"soft": 0.5, "hard": 0.05, "half": 0.2}[kind]
+    rng = np.random.default_rng(21)
+    ny, nx = 13, 11
+    blocks = []
+    for r in range(P):
+        A = rng.standard_normal((ny, nx))
+        if np.issubdtype(dtype, np.complexfloating):
+            A = A + 1j * rng.standard_normal((ny, nx))
+        blocks.append(A.astype(dtype))
+    xtrue = np.zeros(P * nx, dtype=dtype)
+    k = max(2, P * nx // 5)
+    xtrue[rng.permutation(P * nx)[:k]] = rng.standard_normal(k) * 3
+    lam = max(np.linalg.norm(b, 2) ** 2 for b in blocks)
+    return P, solver, kind, dtype, eps, blocks, xtrue, lam
+
+
+def test_sparse_inventory():
+    assert len(SPARSE_CASES) == 3 * 2 * 5
+
+
+@pytest.mark.parametrize("case", SPARSE_CASES)
+def test_oracle_ista_fista(case):
+    import scipy.linalg
+    P, solver, kind, dtype, eps, blocks, xtrue, lam = sparse_inputs(case)
+    np.testing.assert_allclose(lam, GOLD[case + "/lam"], rtol=1e-6)
+    A = scipy.linalg.block_diag(*blocks).astype(dtype)
+    y = A @ xtrue
+    x, iiter, cost = o.ista(A, y, np.zeros_like(xtrue), 40, eps, 1.0 / float(GOLD[case + "/lam"]), 1e-10, kind,
+                            fista=(solver == "fista"))
+    tol = 5e-4 if dtype == np.float32 else 1e-9
+    assert iiter == int(GOLD[case + "/iiter"])
+    np.testing.assert_allclose(cost, GOLD[case + "/cost"], rtol=tol)
+    np.testing.assert_allclose(x, GOLD[case + "/x"], rtol=tol, atol=tol)
+    eig = o.power_iteration(A.conj().T @ A, 300, 1e-13)[0]
+    np.testing.assert_allclose(np.abs(eig), GOLD[case + "/maxeig"], rtol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", SPARSE_CASES)
+def test_gpu_ista_fista_vs_reference(pm, case):
+    P, solver, kind, dtype, eps, blocks, xtrue, lam = sparse_inputs(case)
+    # one rank here: all P blocks stacked in this rank's MPIBlockDiag (same global operator, row-block layout)
+    Op = pm.MPIBlockDiag([pm.local.MatrixMult(torch_from(b), dtype=dtype) for b in blocks])
+    y = Op @ pm.DistributedArray.to_dist(xtrue)
+    x0 = pm.DistributedArray.to_dist(np.zeros_like(xtrue))
+    fn = pm.ista if solver == "ista" else pm.fista
+    alpha = 1.0 / float(GOLD[case + "/lam"])
+    x, iiter, cost = fn(Op, y, x0, niter=40, eps=eps, alpha=alpha, tol=1e-10, threshkind=kind)
+    tol = 2e-3 if dtype == np.float32 else 1e-9
+    assert iiter == int(GOLD[case + "/iiter"])
+    np.testing.assert_allclose(cost, GOLD[case + "/cost"], rtol=tol)
+    np.testing.assert_allclose(host(x.asarray()), GOLD[case + "/x"], rtol=tol, atol=tol)
+    # generic (unfused) execution mode gives the same numbers: SOp = identity operator
+    Iop = pm.MPIBlockDiag([pm.local.Identity(len(xtrue), dtype=dtype)])
+    x2, iiter2, cost2 = fn(Op, y, x0, niter=40, SOp=Iop, eps=eps, alpha=alpha, tol=1e-10, threshkind=kind)
+    assert iiter2 == iiter
+    np.testing.assert_allclose(cost2, cost, rtol=tol)
+    np.testing.assert_allclose(host(x2.asarray()), host(x.asarray()), rtol=tol, atol=tol)
+    # step size from the power iteration (alpha=None)
+    eig = pm.power_iteration(Op.H @ Op, niter=300, tol=1e-13, dtype=dtype,
+                             b_k=pm.DistributedArray(global_shape=len(xtrue), dtype=dtype))[0]
+    np.testing.assert_allclose(np.abs(eig), GOLD[case + "/maxeig"], rtol=1e-3)
