@@ -375,3 +375,14 @@ def test_gemm_bf16_kernel_variants(variant):
     r = subprocess.run([sys.executable, os.path.join(here, "gemm2cta_worker.py")], capture_output=True, text=True,
                        timeout=240, env=dict(os.environ, B2_GEMM_2CTA=variant))
     assert r.returncode == 0 and "GEMM2CTA_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.gpu
+def test_c_abi_client(tmp_path):
+    """plain-C99 program (tests/abi/abi_smoke.c) drives the host-buffer plugin entry point through the C ABI"""
+    import subprocess
+    from test_host_logic import _build_c_client
+    exe = _build_c_client(tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "max |err|" in res.stdout

@@ -153,3 +153,28 @@ def test_comm_shim_world_size_2_gloo(tmp_path):
                        capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("WORKER_OK") == 2
+
+
+# ---- the boundary is a C ABI: a plain-C99 client must compile against the header and link the library ------------
+def _build_c_client(tmp_path):
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "pylops_mpi_b200")
+    exe = str(tmp_path / "abi_smoke")
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "abi", "abi_smoke.c"), "-o", exe, "-L", libdir, "-lb200lops", "-lm",
+                    f"-Wl,-rpath,{libdir}"], check=True, timeout=120)
+    return exe
+
+
+def test_c99_client_compiles_and_fails_loudly_without_gpu(tmp_path):
+    import subprocess
+    import torch
+    exe = _build_c_client(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: covered by the gpu test")
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 2 and "b2_ctx_create" in res.stderr     # no CPU fallback: the product path needs the GPU
