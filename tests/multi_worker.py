@@ -291,6 +291,44 @@ for ny, nx in [(11, 11), (31, 11)]:
     check("cgls x", host(xinv.local_array), xo.locs[rank], 1e-6, 1e-6 * np.abs(xt).max())
     check("cgls cost", cost, cost_o, 1e-5, 1e-7 * cost_o[0])
 
+# ---- "next" rows: MPIGradient / stacked arrays (vs dense per-axis derivatives) ------------------------------------
+for dims, samp in [((16 * P + 3, 11), (1.0, 0.5)), ((8 * P + 1, 6, 7), (0.4, 1.0, 2.0))]:
+    for kind, edge in (("centered", True), ("forward", False)):
+        n = int(np.prod(dims))
+        xg = comm.bcast(rng.normal(0, 10, n), 0)
+        Gop = pm.MPIGradient(dims, sampling=samp, kind=kind, edge=edge)
+        yst = Gop.matvec(pm.DistributedArray.to_dist(xg))
+        refs = [o.derivative_along_axis(xg.reshape(dims), ax, o.first_derivative_dense(dims[ax], samp[ax], kind, edge, 3))
+                for ax in range(len(dims))]
+        for ax in range(len(dims)):
+            check(f"gradient {dims} ax{ax}", host(yst[ax].asarray()), refs[ax].ravel(), 1e-12, 1e-10)
+        refa = sum(o.derivative_along_axis(refs[ax], ax, o.first_derivative_dense(dims[ax], samp[ax], kind, edge, 3).T)
+                   for ax in range(len(dims)))
+        check(f"gradientH {dims}", host(Gop.rmatvec(yst).asarray()), refa.ravel(), 1e-11, 1e-9)
+        flat = np.concatenate([r.ravel() for r in refs])
+        check("stacked dot", yst.dot(yst)[0], np.dot(flat, flat), 1e-12, 0)
+        check("stacked norm", yst.norm()[0], np.linalg.norm(flat), 1e-12, 0)
+
+# ---- "next" row: ISTA / FISTA on BlockDiag (fused one-pass update + one all-reduce per iteration) vs the oracle ---
+import scipy.linalg  # noqa: E402
+for solver, fn in (("ista", pm.ista), ("fista", pm.fista)):
+    for kind, eps in (("soft", 0.5), ("hard", 0.05)):
+        rs = np.random.default_rng(21)
+        ny, nx = 13, 11
+        blocks = [rs.standard_normal((ny, nx)) for _ in range(P)]
+        xtrue = np.zeros(P * nx)
+        xtrue[rs.permutation(P * nx)[:max(2, P * nx // 5)]] = rs.standard_normal(max(2, P * nx // 5)) * 3
+        alpha = 1.0 / max(np.linalg.norm(b, 2) ** 2 for b in blocks)
+        Op = pm.MPIBlockDiag([pm.MatrixMult(blocks[rank])])
+        ysp = Op @ pm.DistributedArray.to_dist(xtrue)
+        xs, its, cs = fn(Op, ysp, pm.DistributedArray.to_dist(np.zeros(P * nx)), niter=30, eps=eps, alpha=alpha,
+                         tol=1e-10, threshkind=kind)
+        Ad = scipy.linalg.block_diag(*blocks)
+        xo, ito, co = o.ista(Ad, Ad @ xtrue, np.zeros(P * nx), 30, eps, alpha, 1e-10, kind, fista=(solver == "fista"))
+        assert its == ito
+        check(f"{solver} {kind} x", host(xs.asarray()), xo, 1e-9, 1e-9)
+        check(f"{solver} {kind} cost", cs, co, 1e-9, 0)
+
 comm.Barrier()
 torch.cuda.synchronize()
 print(f"MULTI_WORKER_OK rank={rank} size={P}")
