@@ -1,6 +1,6 @@
-"""Multi-GPU parity: launches tests/multi_worker.py with one rank per GPU
-(2 ranks, and 4 when the box has them -- 4 also covers the square-grid
-MPIMatrixMult paths).  Skipped on a single-GPU box."""
+"""Multi-rank parity: launches tests/multi_worker.py under torchrun with one rank per GPU.  World size 1 runs
+on any GPU box (the whole worker through the torchrun/NCCL-less path); 2 / 4 / 8 need that many GPUs
+(4 also covers the square-grid MPIMatrixMult paths) and are skipped otherwise."""
 import os
 import subprocess
 import sys
@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("nproc", [2, 4, 8])
+@pytest.mark.parametrize("nproc", [1, 2, 4, 8])
 def test_multi_rank_parity(nproc):
     if torch.cuda.device_count() < nproc:
         pytest.skip(f"needs {nproc} GPUs, box has {torch.cuda.device_count()}")
