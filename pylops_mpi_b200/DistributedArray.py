@@ -623,3 +623,12 @@ class DistributedArray(DistributedMixIn):
                f"local shape={self.local_shape}" \
                f", dtype={self.dtype}, " \
                f"processes={[i for i in range(self.size)]})> "
+
+
+def __getattr__(name):
+    # import-path parity: the reference defines StackedDistributedArray in this module (DistributedArray.py:962);
+    # here it lives in StackedArray.py, which imports this module -> resolve lazily
+    if name == "StackedDistributedArray":
+        from .StackedArray import StackedDistributedArray
+        return StackedDistributedArray
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

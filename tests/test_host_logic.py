@@ -178,3 +178,32 @@ def test_c99_client_compiles_and_fails_loudly_without_gpu(tmp_path):
         pytest.skip("GPU present: covered by the gpu test")
     res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert res.returncode == 2 and "b2_ctx_create" in res.stderr     # no CPU fallback: the product path needs the GPU
+
+
+def test_reference_import_paths_and_names():
+    """a pylops-mpi user switching packages finds the same module paths / public names (reference
+    pylops_mpi/__init__.py, basicoperators/__init__.py:22-47, optimization/, signalprocessing/, waveeqprocessing/)"""
+    import importlib
+    pm = importlib.import_module("pylops_mpi_b200")
+    for name in ("DistributedArray", "Partition", "StackedDistributedArray", "MPILinearOperator", "asmpilinearoperator",
+                 "MPIStackedLinearOperator", "MPIMatrixMult", "MPIBlockDiag", "MPIStackedBlockDiag", "MPIVStack",
+                 "MPIStackedVStack", "MPIHStack", "MPIFirstDerivative", "MPISecondDerivative", "MPILaplacian",
+                 "MPIGradient", "MPIFredholm1", "MPIMDC", "cg", "cgls", "ista", "fista", "dottest"):
+        assert hasattr(pm, name), name
+    for mod, names in (("basicoperators", ("MPIMatrixMult", "MPIBlockDiag", "MPIStackedBlockDiag", "MPIVStack",
+                                           "MPIStackedVStack", "MPIHStack", "MPIFirstDerivative", "MPISecondDerivative",
+                                           "MPILaplacian", "MPIGradient")),
+                       ("basicoperators.Gradient", ("MPIGradient",)),
+                       ("basicoperators.MatrixMult", ("MPIMatrixMult", "active_grid_comm", "local_block_split", "block_gather")),
+                       ("StackedLinearOperator", ("MPIStackedLinearOperator",)),
+                       ("LinearOperator", ("MPILinearOperator", "asmpilinearoperator")),
+                       ("DistributedArray", ("DistributedArray", "Partition", "local_split", "StackedDistributedArray")),
+                       ("signalprocessing", ("MPIFredholm1",)), ("signalprocessing.Fredholm1", ("MPIFredholm1",)),
+                       ("waveeqprocessing", ("MPIMDC",)), ("waveeqprocessing.MDC", ("MPIMDC",)),
+                       ("optimization.basic", ("cg", "cgls")), ("optimization.cls_basic", ("CG", "CGLS")),
+                       ("optimization.sparsity", ("ista", "fista")), ("optimization.cls_sparsity", ("ISTA", "FISTA")),
+                       ("optimization.eigs", ("power_iteration",)), ("utils.dottest", ("dottest",)),
+                       ("utils.decorators", ("reshaped",))):
+        m = importlib.import_module("pylops_mpi_b200." + mod)
+        for n in names:
+            assert hasattr(m, n), f"{mod}.{n}"
