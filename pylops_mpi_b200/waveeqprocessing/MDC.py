@@ -3,8 +3,9 @@
 :class:`MPIFredholm1` (fused product + all-gather kernel); the FFT / frequency-truncation stages are
 rank-replicated local operators (``local.FFT``, ``local.Identity``) wrapped in ``MPILinearOperator``,
 exactly as the reference composes third-party pylops operators.  The reference has no MDC test and
-pylops is not available here: the FFT stage's convention is restated (see ``local.FFT``) and the
-pipeline's parity is UNPINNED (checked against the same restatement in the oracle + dottest)."""
+pylops is not available here: the FFT stage's convention is restated (see ``local.FFT``); the pipeline is
+checked against fixtures produced by the reference's own chain run over that restatement in NumPy
+(tests/golden ``mdc/``), the oracle and a dot-test."""
 from __future__ import annotations
 
 import logging

@@ -36,7 +36,7 @@ def load_reference():
     pkg.MPIStackedLinearOperator = slo.MPIStackedLinearOperator
     # sub-packages: register bare namespaces so their __init__ (which pulls in operators that need
     # more of third-party pylops than this path uses) is not executed
-    for sub in ("basicoperators", "signalprocessing", "optimization"):
+    for sub in ("basicoperators", "signalprocessing", "optimization", "waveeqprocessing"):
         m = types.ModuleType("pylops_mpi." + sub)
         m.__path__ = [os.path.join(REF, "pylops_mpi", sub)]
         sys.modules["pylops_mpi." + sub] = m
@@ -48,7 +48,8 @@ def load_reference():
         mods[name.split(".")[-1]] = importlib.import_module("pylops_mpi." + name)
     bo = sys.modules["pylops_mpi.basicoperators"]
     bo.MPIBlockDiag, bo.MPISecondDerivative = mods["BlockDiag"].MPIBlockDiag, mods["SecondDerivative"].MPISecondDerivative
-    for name in ("basicoperators.Gradient", "basicoperators.Laplacian", "optimization.eigs", "optimization.cls_sparsity"):  # "next" rows: the reference's own glue over
+    for name in ("basicoperators.Gradient", "basicoperators.Laplacian", "optimization.eigs", "optimization.cls_sparsity",
+                 "waveeqprocessing.MDC"):  # "next" rows: the reference's own glue over
         mods[name.split(".")[-1]] = importlib.import_module("pylops_mpi." + name)  # refshim/pylops/_derivatives.py
     return pkg, mods
 
@@ -344,6 +345,34 @@ def main():
                 res = MPI.run_world(P, t_sparse, P, solver, threshkind, dtype, 40, eps)[0]
                 for k, v in res.items():
                     put(f"sparse/P{P}/{solver}/{threshkind}/{np.dtype(dtype).name}/{k}", v)
+
+    # ---- MPIMDC ("next" row f1; the reference's chain F1^H I1^H MPIFredholm1 I F over refshim's restated FFT) ------
+    MDC = mods["MDC"].MPIMDC
+
+    def t_mdc(rank, P, twosided, dtype, conj, prescaled):
+        rng = np.random.default_rng(31)
+        ns, nr, nv, nt = 6, 5, 3, (31 if twosided else 32)
+        nfmax = int(np.ceil((nt + 1) / 2)) - 3
+        G = (rng.standard_normal((nfmax, ns, nr)) + 1j * rng.standard_normal((nfmax, ns, nr))).astype(dtype)
+        rdt = np.real(np.ones(1, dtype)).dtype
+        m = rng.standard_normal(nt * nr * nv).astype(rdt)
+        d = rng.standard_normal(nt * ns * nv).astype(rdt)
+        ext = [nfmax // P + (1 if r < nfmax % P else 0) for r in range(P)]
+        off = np.cumsum([0] + ext)
+        Mop = MDC(G[off[rank]:off[rank + 1]], nt=nt, nv=nv, nfreq=nfmax, dt=0.004, dr=2.0, twosided=twosided,
+                  conj=conj, prescaled=prescaled)
+        y = Mop @ DA.to_dist(m, partition=Partition.BROADCAST)
+        xa = Mop.H @ DA.to_dist(d, partition=Partition.BROADCAST)
+        return {"G": G, "m": m, "d": d, "y": y.local_array, "xa": xa.local_array}
+
+    for P in (1, 2, 3):
+        for twosided in (True, False):
+            for dtype, conj, prescaled in ((np.complex128, False, False), (np.complex128, True, True), (np.complex64, False, False)):
+                res = MPI.run_world(P, t_mdc, P, twosided, dtype, conj, prescaled)
+                for k, v in res[0].items():
+                    put(f"mdc/P{P}/t{int(twosided)}/{np.dtype(dtype).name}/c{int(conj)}p{int(prescaled)}/{k}", v)
+                for r in range(1, P):      # BROADCAST outputs: identical on every rank
+                    assert np.array_equal(res[r]["y"], res[0]["y"]) and np.array_equal(res[r]["xa"], res[0]["xa"])
 
     path = os.path.join(HERE, os.environ.get("GOLDEN_OUT", "reference_golden.npz"))
     np.savez_compressed(path, **out)

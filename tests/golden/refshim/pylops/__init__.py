@@ -29,6 +29,31 @@ class MatrixMult(LinearOperator):
         return self.A.conj().T @ x
 
 
+class Identity(LinearOperator):
+    """pylops.Identity(N, M): keep the first N of M samples (adjoint: zero-pad) -- restated third-party operator"""
+
+    def __init__(self, N, M=None, inplace=True, dtype="float64"):
+        M = N if M is None else M
+        self.inplace = inplace
+        super().__init__(dtype=np.dtype(dtype), shape=(int(N), int(M)))
+
+    def _matvec(self, x):
+        N, M = self.shape
+        if N <= M:
+            return x[:N] if self.inplace else x[:N].copy()
+        y = np.zeros(N, dtype=self.dtype)
+        y[:M] = x
+        return y
+
+    def _rmatvec(self, x):
+        N, M = self.shape
+        if M <= N:
+            return x[:M] if self.inplace else x[:M].copy()
+        y = np.zeros(M, dtype=self.dtype)
+        y[:N] = x
+        return y
+
+
 from . import utils, optimization  # noqa: E402,F401
 from ._derivatives import FirstDerivative, SecondDerivative  # noqa: E402,F401
-from . import basicoperators  # noqa: E402,F401
+from . import basicoperators, signalprocessing  # noqa: E402,F401

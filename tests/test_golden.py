@@ -544,3 +544,50 @@ def test_gpu_ista_fista_vs_reference(pm, case):
     eig = pm.power_iteration(Op.H @ Op, niter=300, tol=1e-13, dtype=dtype,
                              b_k=pm.DistributedArray(global_shape=len(xtrue), dtype=dtype))[0]
     np.testing.assert_allclose(np.abs(eig), GOLD[case + "/maxeig"], rtol=1e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" row f1: MPIMDC -- the reference's chain (MDC.py) over refshim's restated pylops FFT / Identity
+# ---------------------------------------------------------------------------------------------
+MDC_CASES = cases("mdc", 5)
+
+
+def mdc_inputs(case):
+    _, P, t, dt, cp = case.split("/")
+    P, twosided, conj, prescaled = int(P[1:]), bool(int(t[1:])), bool(int(cp[1])), bool(int(cp[3]))
+    G, m, d = GOLD[case + "/G"], GOLD[case + "/m"], GOLD[case + "/d"]
+    nt = 31 if twosided else 32
+    nf = G.shape[0]
+    off = np.cumsum([0] + [nf // P + (1 if r < nf % P else 0) for r in range(P)])
+    return P, twosided, conj, prescaled, G, m, d, nt, off
+
+
+def test_mdc_inventory():
+    assert len(MDC_CASES) == 3 * 2 * 3
+
+
+@pytest.mark.parametrize("case", MDC_CASES)
+def test_oracle_mdc(case):
+    P, twosided, conj, prescaled, G, m, d, nt, off = mdc_inputs(case)
+    Gl = [G[off[r]:off[r + 1]].astype(np.complex128) for r in range(P)]
+    kw = dict(dt=0.004, dr=2.0, prescaled=prescaled, conj=conj)
+    y = o.mdc(Gl, m.astype(np.float64), nt, 3, twosided, False, **kw)
+    xa = o.mdc(Gl, d.astype(np.float64), nt, 3, twosided, True, **kw)
+    gy, gxa = GOLD[case + "/y"], GOLD[case + "/xa"]
+    assert np.abs(gy.imag).max() == 0 and np.abs(gxa.imag).max() == 0
+    tol = 2e-6 if G.dtype == np.complex64 else 1e-13
+    np.testing.assert_allclose(y, gy.real, rtol=tol, atol=tol * np.abs(gy).max())
+    np.testing.assert_allclose(xa, gxa.real, rtol=tol, atol=tol * np.abs(gxa).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", MDC_CASES)
+def test_gpu_mdc_vs_reference(pm, case):
+    P, twosided, conj, prescaled, G, m, d, nt, off = mdc_inputs(case)
+    Mop = pm.MPIMDC(G, nt=nt, nv=3, nfreq=G.shape[0], dt=0.004, dr=2.0, twosided=twosided, conj=conj, prescaled=prescaled)
+    y = Mop @ pm.DistributedArray.to_dist(m, partition=pm.Partition.BROADCAST)
+    xa = Mop.H @ pm.DistributedArray.to_dist(d, partition=pm.Partition.BROADCAST)
+    gy, gxa = GOLD[case + "/y"].real, GOLD[case + "/xa"].real
+    tol = 2e-4 if G.dtype == np.complex64 else 1e-11
+    np.testing.assert_allclose(host(y.asarray()).real, gy, rtol=tol, atol=tol * np.abs(gy).max())
+    np.testing.assert_allclose(host(xa.asarray()).real, gxa, rtol=tol, atol=tol * np.abs(gxa).max())

@@ -343,7 +343,7 @@ def test_matrixmult_bf16(pm, kind, M):
     assert np.all(erra <= (np.abs(A64.T) @ np.abs(yb)) * N * 6e-8 + 1e-6)
 
 
-# ---- MPIMDC ("next" row f1; parity UNPINNED: checked against the oracle's restatement + dottest) ------
+# ---- MPIMDC ("next" row f1; reference-chain fixtures are in test_golden.py; here: oracle + adjointness) ------
 @pytest.mark.parametrize("twosided", [True, False])
 @pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
 def test_mdc_pipeline(pm, twosided, dtype):
