@@ -510,14 +510,19 @@ def run_extras(pm, L, comm, peaks, args):
                     sizes = [(Kg // Pr) * (Mg // Pc)] * size
                     xs = pm.DistributedArray(global_shape=Kg * Mg, local_shapes=sizes, dtype=np.float32)
                     xs.local_array.normal_()
-                    ms = time_loop(lambda: Sop.matvec(xs), 5, 2, comm)
+                    # sub-millisecond applies (M = 1 / Pc) need more launches to reach a steady state: with 5 timed
+                    # steps the first, cold ones dominated (0.53 ms reported vs 0.35 ms steady, profiles/r01_diag_matmul_m1.json)
+                    kk, ww = (5, 2) if Mg > 64 else (20, 5)
+                    ms = time_loop(lambda: Sop.matvec(xs), kk, ww, comm)
                     fl = 2.0 * Ng * Kg * Mg
                     key = f"{'replicated' if rep else 'summa'}_bf16_32768_M{Mg}_grid{Pr}x{Pc}"
-                    out[key] = {"TF/s": fl * 5 / (ms * 1e-3) / 1e12, "ms": ms / 5,
-                                "frac_tensor_total": fl * 5 / (ms * 1e-3) / 1e12 / (size * peaks.get("bf16_tflops", 1590.0)),
-                                "GB/s_A": 2.0 * Ng * Kg * 5 / (ms * 1e-3) / 1e9}
-                    ms = time_loop(lambda: Sop.rmatvec(Sop.matvec(xs)), 3, 1, comm)
-                    out[key]["fwd+adj_ms"] = ms / 3
+                    out[key] = {"TF/s": fl * kk / (ms * 1e-3) / 1e12, "ms": ms / kk,
+                                "frac_tensor_total": fl * kk / (ms * 1e-3) / 1e12 / (size * peaks.get("bf16_tflops", 1590.0)),
+                                "GB/s_A": 2.0 * Ng * Kg * kk / (ms * 1e-3) / 1e9,
+                                "frac_hbm_A": 2.0 * Ng * Kg * kk / (ms * 1e-3) / 1e9 / (size * hbm)}
+                    k2, w2 = (3, 1) if Mg > 64 else (10, 3)
+                    ms = time_loop(lambda: Sop.rmatvec(Sop.matvec(xs)), k2, w2, comm)
+                    out[key]["fwd+adj_ms"] = ms / k2
                     del Sop, xs
             del At
     except Exception as exc:
