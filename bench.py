@@ -512,7 +512,10 @@ def run_extras(pm, L, comm, peaks, args):
                     xs.local_array.normal_()
                     # sub-millisecond applies (M = 1 / Pc) need more launches to reach a steady state: with 5 timed
                     # steps the first, cold ones dominated (0.53 ms reported vs 0.35 ms steady, profiles/r01_diag_matmul_m1.json)
-                    kk, ww = (5, 2) if Mg > 64 else (20, 5)
+                    kk, ww = (5, 2) if Mg > 64 else (20, 10)
+                    if Mg <= 64:        # let the power cap recover after the tensor-core runs (HBM-bound GEMV follows)
+                        torch.cuda.synchronize()
+                        time.sleep(0.5)
                     ms = time_loop(lambda: Sop.matvec(xs), kk, ww, comm)
                     fl = 2.0 * Ng * Kg * Mg
                     key = f"{'replicated' if rep else 'summa'}_bf16_32768_M{Mg}_grid{Pr}x{Pc}"
