@@ -5,11 +5,19 @@ imported unmodified) under the in-process MPI shim in tests/golden/refshim/.
 
 Runs only in the build container (the GPU box has no /root/reference); the
 .npz it writes is committed and is what tests/test_golden.py checks the oracle
-and the CUDA path against.  Third-party ``pylops`` is absent from the image:
-its only arithmetic on this path (the dense block ``A @ x``) is restated in
+and the CUDA path against.  Third-party ``pylops`` is absent from the image.  On
+the hot path its only arithmetic (the dense block ``A @ x``) is restated in
 refshim/pylops; mpi4py is replaced by threads.  Everything else -- partition
 bookkeeping, @reshaped, ghost cells, the stencils, BlockDiag/VStack/MatrixMult/
 Fredholm1, dot/norm, CGLS, dottest -- is the reference's own code.
+For the "next" rows more of pylops had to be restated (published formulas, marked
+as such in refshim/pylops): the rank-local First/SecondDerivative used by
+MPIGradient/MPILaplacian, the soft/hard/half thresholds used by ISTA/FISTA, and
+the numpy FFT / Identity used by MPIMDC; the distributed glue and the solver
+loops around them are still the reference's own code.
+Not reproducible bit for bit: ``sparse/*/maxeig`` (the reference's power iteration
+draws its start vector from the process-global NumPy RNG, which the rank threads
+share); tests compare it with rtol 1e-3 only.
 """
 import importlib
 import os
