@@ -41,10 +41,13 @@ enum { B2_THRESH_NONE = 0, B2_THRESH_SOFT = 1, B2_THRESH_HARD = 2, B2_THRESH_HAL
 enum { B2_OK = 0, B2_ERR_DTYPE = 2001, B2_ERR_ARG = 2002, B2_ERR_HALO = 2003,
        B2_ERR_WORKSPACE = 2004, B2_ERR_UNSUPPORTED = 2005, B2_ERR_ALIGN = 2006 };
 
-typedef struct b2_ctx b2_ctx;    /* per-device context: SM count, reduction workspace */
-typedef struct b2_comm b2_comm;  /* one NCCL communicator (world, mask group, grid row / col) */
-typedef struct b2_peer b2_peer;
-typedef struct b2_peer_vec b2_peer_vec;  /* peer-memory mailboxes for one-shot VECTOR all-reduces */  /* peer-memory mailbox group for one-shot scalar all-reduces */
+/* per-device context: SM count + the reduction workspace (per-CTA partials, ticket counter) shared by b2_dot /
+ * b2_norm_partial / b2_dot_multi / b2_sparse_update / the transposed b2_gemv.  Calls that use the workspace must be
+ * stream-ordered with respect to each other: use one b2_ctx per stream that issues reductions concurrently. */
+typedef struct b2_ctx b2_ctx;
+typedef struct b2_comm b2_comm;          /* one NCCL communicator (world, mask group, grid row / col) */
+typedef struct b2_peer b2_peer;          /* peer-memory mailbox group for one-shot SCALAR all-reduces */
+typedef struct b2_peer_vec b2_peer_vec;  /* peer-memory mailboxes for one-shot VECTOR all-reduces */
 
 int b2_version(void);
 const char* b2_strerror(int code);
