@@ -10,7 +10,6 @@ allreduce of shapes for every temporary it creates (:345-358, :523-539).
 """
 from __future__ import annotations
 
-import ctypes as C
 from enum import Enum
 from numbers import Integral
 from typing import List, Optional, Sequence, Tuple, Union

@@ -5,7 +5,7 @@ of results runs in libb200lops kernels.
 """
 from __future__ import annotations
 
-from typing import Callable, Optional
+from typing import Callable
 
 import numpy as np
 

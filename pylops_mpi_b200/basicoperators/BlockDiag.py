@@ -8,7 +8,6 @@ from typing import List, Optional, Sequence
 import numpy as np
 import torch
 
-from .. import _lib
 from ..comm import COMM_WORLD, resolve
 from ..DistributedArray import DistributedArray
 from ..LinearOperator import MPILinearOperator, _get_dtype

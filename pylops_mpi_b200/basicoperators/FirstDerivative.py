@@ -10,7 +10,6 @@ exchange.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Callable, Union
 
 import numpy as np
 import torch

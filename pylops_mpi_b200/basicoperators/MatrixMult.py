@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..comm import COMM_WORLD, Comm, resolve, SUM
+from ..comm import COMM_WORLD, resolve, SUM
 from ..Distributed import DistributedMixIn, allreduce_, allgatherv, bcast_, group, send, recv
 from ..DistributedArray import DistributedArray, Partition
 from ..LinearOperator import MPILinearOperator

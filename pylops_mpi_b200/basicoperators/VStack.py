@@ -7,7 +7,6 @@ from __future__ import annotations
 from typing import Sequence
 
 import numpy as np
-import torch
 
 from ..comm import COMM_WORLD, resolve, SUM
 from ..Distributed import allreduce_

@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import sys
 import time
-from typing import Callable, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence
 
 import numpy as np
 import torch

@@ -9,7 +9,6 @@ import torch
 
 from .. import _lib
 from ..comm import COMM_WORLD, resolve
-from ..Distributed import allgatherv
 from ..DistributedArray import DistributedArray, Partition
 from ..LinearOperator import MPILinearOperator
 
