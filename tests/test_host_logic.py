@@ -207,3 +207,41 @@ def test_reference_import_paths_and_names():
         m = importlib.import_module("pylops_mpi_b200." + mod)
         for n in names:
             assert hasattr(m, n), f"{mod}.{n}"
+
+
+# ---- property tests of the integer bookkeeping (bit-exact rows a1 / a8) -----------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.lists(st.integers(0, 50), min_size=1, max_size=9), st.data())
+def test_repartition_plan_property(src, data):
+    """any source partition -> any destination partition of the same total: every element moves exactly once,
+    sends and receives pair up, nothing is sent to oneself twice"""
+    from pylops_mpi_b200.utils.partition import repartition_plan
+    P, n = len(src), sum(src)
+    cuts = sorted(data.draw(st.lists(st.integers(0, n), min_size=P - 1, max_size=P - 1)))
+    dst = [b - a for a, b in zip([0] + cuts, cuts + [n])]
+    x = np.arange(n)
+    xs = np.split(x, np.cumsum(src)[:-1])
+    out = [np.full(d, -1) for d in dst]
+    for r in range(P):
+        sends, recvs = repartition_plan(src, dst, r)
+        assert sum(c for _, _, c in sends) == src[r] and sum(c for _, _, c in recvs) == dst[r]
+        assert len({p for p, _, _ in sends}) == len(sends) and len({p for p, _, _ in recvs}) == len(recvs)
+        for peer, off, cnt in sends:
+            assert cnt > 0
+            back = [q for q in repartition_plan(src, dst, peer)[1] if q[0] == r]
+            assert len(back) == 1 and back[0][2] == cnt
+            out[peer][back[0][1]:back[0][1] + cnt] = xs[r][off:off + cnt]
+    assert np.array_equal(np.concatenate(out) if n else np.zeros(0, int), x)
+
+
+@settings(max_examples=200, deadline=None)
+@given(st.integers(0, 10 ** 7), st.integers(1, 64))
+def test_local_split_sizes_property(n, P):
+    from pylops_mpi_b200.utils.partition import local_split_sizes, offsets
+    s = local_split_sizes(n, P)
+    assert len(s) == P and sum(s) == n and max(s) - min(s) <= 1 and s == sorted(s, reverse=True)
+    off = offsets(s)
+    assert off[0] == 0 and off[-1] == n and len(off) == P + 1
