@@ -530,6 +530,27 @@ def run_extras(pm, L, comm, peaks, args):
             del At
     except Exception as exc:
         out["summa_bf16_32768"] = {"error": repr(exc)}
+    if size > 1:
+        # BASELINE config 4 (i), the literal "32768-vec": 1-D row panels (grid P x 1, replicated mode) read every byte of A
+        # exactly once per apply -- the 2-D grids above re-read A Pc times when M < Pc
+        try:
+            Ng = Kg = 32768
+            At = (torch.randn(Ng // size, Kg, device="cuda",
+                              generator=torch.Generator(device="cuda").manual_seed(1 + rank)) / 181).to(torch.bfloat16)
+            Sop = pm.MPIMatrixMult(At, 1, kind="summa", dtype="bfloat16", grid=(size, 1), replicate=True)
+            xs = pm.DistributedArray(global_shape=Kg, local_shapes=[Kg // size] * size, dtype=np.float32)
+            xs.local_array.normal_()
+            torch.cuda.synchronize()
+            time.sleep(0.5)
+            ms = time_loop(lambda: Sop.matvec(xs), 20, 10, comm)
+            gb = 2.0 * Ng * Kg * 20 / (ms * 1e-3) / 1e9
+            out[f"replicated_bf16_32768_M1_grid{size}x1"] = {"ms": ms / 20, "GB/s_A": gb, "frac_hbm_A": gb / (size * hbm),
+                                                             "GF/s": 2.0 * Ng * Kg * 20 / (ms * 1e-3) / 1e9}
+            ms = time_loop(lambda: Sop.rmatvec(Sop.matvec(xs)), 10, 3, comm)
+            out[f"replicated_bf16_32768_M1_grid{size}x1"]["fwd+adj_ms"] = ms / 10
+            del Sop, xs, At
+        except Exception as exc:
+            out[f"replicated_bf16_32768_M1_grid{size}x1"] = {"error": repr(exc)}
     # --- config 5: Fredholm1 (64 slices per GPU, 256 x 256 x 64, complex64) -------------------
     nsl, ns, nr, nv = 64, 256, 256, 64
     G = torch.randn(nsl, ns, nr, device="cuda", dtype=torch.complex64)
