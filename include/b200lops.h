@@ -170,6 +170,20 @@ int b2_batched_gemm(b2_ctx* ctx, const void* G, const void* x, void* y, size_t n
 int b2_batched_gemm_allgather(b2_ctx* ctx, const void* G, const void* x, void* y, void* const* peers_host,
                               int npeers, size_t nsl, size_t nx, size_t ny, size_t nz, int adjoint,
                               int dtype, void* stream);
+/* Tensor-core (tcgen05) plan for the same product, float32 / complex64 only (Fredholm1.py:119-129, 147-167).
+ * G is operator state: plan creation splits G and G^H (the reference's `saveGt`, :105-106) ONCE into three bf16
+ * planes each ("bf16x3": 24 significant bits, six MMAs per k-step -> float32-class accuracy on the bf16 tensor
+ * pipe); complex64 runs as one real product over the (re,im)-interleaved views.  b2_fredholm_apply packs x
+ * (one small kernel) and runs the batched product; with npeers > 0 the epilogue also stores every output
+ * element to the same offset of the peers' IPC-mapped buffers (fused Allgather of Fredholm1.py:131-132,
+ * completion = any stream-ordered cross-rank barrier after it).  The plan owns its device workspaces; applies
+ * of one plan must be stream-ordered.  G must stay valid only during b2_fredholm_plan_create. */
+typedef struct b2_fredholm_plan b2_fredholm_plan;
+int b2_fredholm_plan_create(b2_ctx* ctx, const void* G, size_t nsl, size_t nx, size_t ny, size_t nz, int dtype,
+                            b2_fredholm_plan** out);
+int b2_fredholm_plan_destroy(b2_fredholm_plan* plan);
+int b2_fredholm_apply(b2_fredholm_plan* plan, const void* x, void* y, void* const* peers_host, int npeers,
+                      int adjoint, void* stream);
 /* peer-mappable device buffers (cudaMalloc) and CUDA IPC handle plumbing (64-byte handles) */
 int b2_symm_alloc(size_t bytes, void** out);
 int b2_symm_free(void* p);

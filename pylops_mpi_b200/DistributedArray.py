@@ -313,11 +313,32 @@ class DistributedArray(DistributedMixIn):
         a = self._local_array
         return a if a.is_contiguous() else a.contiguous()
 
+    def _pair(self, other: "DistributedArray") -> Tuple[torch.Tensor, torch.Tensor]:
+        """contiguous local buffers of ``self`` and ``other`` in their COMMON dtype (NumPy type promotion, as
+        the reference's ``self[:] + other[:]`` does): the single-dtype kernels must never see mixed buffers"""
+        x, y = self._cont(), other._cont()
+        if x.dtype != y.dtype:
+            dt = torch.promote_types(x.dtype, y.dtype)
+            x, y = x.to(dt), y.to(dt)
+        return x, y
+
+    def _as_mine(self, other: "DistributedArray") -> torch.Tensor:
+        """``other``'s contiguous buffer cast to THIS array's dtype (in-place updates keep the left operand's
+        dtype, like NumPy's ``a += b``; complex into real is refused as NumPy refuses it)"""
+        y = other._cont()
+        if y.dtype != self._tdtype:
+            if y.dtype.is_complex and not self._tdtype.is_complex:
+                raise TypeError(f"cannot cast {y.dtype} to {self._tdtype} in an in-place update")
+            y = y.to(self._tdtype)
+        return y
+
     def _lincomb(self, a, x: torch.Tensor, b=None, y: Optional[torch.Tensor] = None,
                  out: Optional[torch.Tensor] = None, conj_x: bool = False) -> torch.Tensor:
         """out = a*op(x) + b*y on the device (b2_lincomb)"""
         if out is None:
             out = torch.empty_like(x)
+        if (y is not None and y.dtype != x.dtype) or out.dtype != x.dtype:
+            raise TypeError(f"b2_lincomb needs one dtype, got {x.dtype} / {None if y is None else y.dtype} / {out.dtype}")
         n = x.numel()
         if n:
             _lib.check(_lib.lib.b2_lincomb(_lib.ctx(), out.data_ptr(), _lib.cpair(a), x.data_ptr(),
@@ -340,13 +361,15 @@ class DistributedArray(DistributedMixIn):
     def __sub__(self, x):
         self._check_partition_shape(x)
         self._check_mask(x)
-        return self._like(self._lincomb(1.0, self._cont(), -1.0, x._cont()))
+        a, b = self._pair(x)
+        out = self._lincomb(1.0, a, -1.0, b)
+        return self._like(out, dtype=out.dtype)
 
     def __isub__(self, x):
         self._check_partition_shape(x)
         self._check_mask(x)
         a = self._cont()
-        self._lincomb(1.0, a, -1.0, x._cont(), out=a)
+        self._lincomb(1.0, a, -1.0, self._as_mine(x), out=a)
         if a is not self._local_array:
             self._local_array.copy_(a)
         return self
@@ -360,13 +383,15 @@ class DistributedArray(DistributedMixIn):
     def add(self, dist_array):
         self._check_partition_shape(dist_array)
         self._check_mask(dist_array)
-        return self._like(self._lincomb(1.0, self._cont(), 1.0, dist_array._cont()))
+        a, b = self._pair(dist_array)
+        out = self._lincomb(1.0, a, 1.0, b)
+        return self._like(out, dtype=out.dtype)
 
     def iadd(self, dist_array):
         self._check_partition_shape(dist_array)
         self._check_mask(dist_array)
         a = self._cont()
-        self._lincomb(1.0, a, 1.0, dist_array._cont(), out=a)
+        self._lincomb(1.0, a, 1.0, self._as_mine(dist_array), out=a)
         if a is not self._local_array:
             self._local_array.copy_(a)
         return self
@@ -375,28 +400,31 @@ class DistributedArray(DistributedMixIn):
         if isinstance(dist_array, DistributedArray):
             self._check_partition_shape(dist_array)
             self._check_mask(dist_array)
-            x, y = self._cont(), dist_array._cont()
+            x, y = self._pair(dist_array)
             out = torch.empty_like(x)
             if x.numel():
                 _lib.check(_lib.lib.b2_mul(_lib.ctx(), out.data_ptr(), x.data_ptr(), y.data_ptr(),
                                            x.numel(), _lib.code(x.dtype), 0, _lib.stream()), "b2_mul")
-            return self._like(out)
+            return self._like(out, dtype=out.dtype)
         scalar = complex(dist_array)
+        x = self._cont()
         if scalar.imag != 0.0 and not self._tdtype.is_complex:
-            raise TypeError("complex scalar times a real DistributedArray")
-        return self._like(self._lincomb(scalar, self._cont()))
+            # NumPy promotes real * complex scalar to the matching complex dtype
+            x = x.to(torch.complex64 if self._tdtype in (torch.float32, torch.bfloat16) else torch.complex128)
+        out = self._lincomb(scalar, x)
+        return self._like(out, dtype=out.dtype)
 
     # fused updates used by the solvers (no temporaries): self <- self + a*x ; self <- x + b*self
     def axpy_(self, a, x: "DistributedArray"):
         s = self._cont()
-        self._lincomb(a, x._cont(), 1.0, s, out=s)
+        self._lincomb(a, self._as_mine(x), 1.0, s, out=s)
         if s is not self._local_array:
             self._local_array.copy_(s)
         return self
 
     def xpby_(self, x: "DistributedArray", b):
         s = self._cont()
-        self._lincomb(1.0, x._cont(), b, s, out=s)
+        self._lincomb(1.0, self._as_mine(x), b, s, out=s)
         if s is not self._local_array:
             self._local_array.copy_(s)
         return self
@@ -421,6 +449,9 @@ class DistributedArray(DistributedMixIn):
     def _dot_device(self, dist_array, vdot: bool = False) -> torch.Tensor:
         """device float64[2] = (re, im) of the global dot product (no host sync)"""
         x, y = self._scatter_view(), dist_array._scatter_view()
+        if x.dtype != y.dtype:                     # NumPy promotes; the kernel takes ONE dtype code
+            dt = torch.promote_types(x.dtype, y.dtype)
+            x, y = x.to(dt), y.to(dt)
         out = torch.empty(2, dtype=torch.float64, device=x.device)
         _lib.check(_lib.lib.b2_dot(_lib.ctx(), x.data_ptr() if x.numel() else None,
                                    y.data_ptr() if y.numel() else None, x.numel(),

@@ -89,6 +89,9 @@ def _load():
         "b2_gemm": ([vp, vp, sz, vp, sz, vp, sz, sz, sz, sz, i, i, i, vp], i),
         "b2_batched_gemm": ([vp, vp, vp, vp, sz, sz, sz, sz, i, i, vp], i),
         "b2_batched_gemm_allgather": ([vp, vp, vp, vp, C.POINTER(vp), i, sz, sz, sz, sz, i, i, vp], i),
+        "b2_fredholm_plan_create": ([vp, vp, sz, sz, sz, sz, i, C.POINTER(vp)], i),
+        "b2_fredholm_plan_destroy": ([vp], i),
+        "b2_fredholm_apply": ([vp, vp, vp, C.POINTER(vp), i, i, vp], i),
         "b2_symm_alloc": ([sz, C.POINTER(vp)], i),
         "b2_symm_free": ([vp], i),
         "b2_ipc_get_handle": ([vp, vp], i),

@@ -18,7 +18,7 @@ OUT = os.path.join(HERE, "libb200lops.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SOURCES = ["ctx.cu", "elementwise.cu", "reduce.cu", "sparsity.cu", "stencil.cu", "gemv.cu", "gemm_simt.cu",
-           "gemm_tc.cu", "gemm_tc2.cu", "host_pipe.cu", "comm.cu", "peer.cu"]
+           "gemm_tc.cu", "gemm_tc2.cu", "fredholm_tc.cu", "host_pipe.cu", "comm.cu", "peer.cu"]
 
 
 def _nccl_paths():
@@ -52,6 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         srcp = os.path.join(CSRC, src)
         if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(srcp)
                 and os.path.getmtime(obj) > os.path.getmtime(os.path.join(CSRC, "common.cuh"))
+                and os.path.getmtime(obj) > os.path.getmtime(os.path.join(CSRC, "tc_ptx.cuh"))
                 and os.path.getmtime(obj) > os.path.getmtime(os.path.join(INCLUDE, "b200lops.h"))):
             continue
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -4,6 +4,8 @@ the slice axis; BROADCAST model in, BROADCAST data out via an NCCL Allgather(v)
 written straight into the output buffer."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -48,6 +50,27 @@ class MPIFredholm1(MPILinearOperator):
         self._fused = bool(fused) and base_comm.Get_size() > 1
         if self._fused:
             self._setup_arenas(base_comm)
+        # tensor-core plan (csrc/fredholm_tc.cu): float32 / complex64 products run on tcgen05 with bf16x3 split
+        # operands (float32-class accuracy); G and G^H planes are built once here.  B2_FREDHOLM_TC=0 keeps the SIMT
+        # kernel, =1 forces the tensor-core path for every shape (tests), default: slices of >= 32768 products.
+        mode = os.environ.get("B2_FREDHOLM_TC", "auto")
+        self._plan = None
+        if self._tdtype in (torch.float32, torch.complex64) and mode != "0" and \
+                (mode == "1" or self.nx * self.ny * self.nz >= 32768) and self.nsl > 0:
+            import ctypes as C
+            h = C.c_void_p()
+            _lib.check(_lib.lib.b2_fredholm_plan_create(_lib.ctx(), self.G.data_ptr(), self.nsl, self.nx, self.ny, self.nz,
+                                                        _lib.code(self._tdtype), C.byref(h)), "b2_fredholm_plan_create")
+            self._plan = h
+
+    def __del__(self):
+        plan = getattr(self, "_plan", None)
+        if plan is not None:
+            try:
+                _lib.lib.b2_fredholm_plan_destroy(plan)
+            except Exception:
+                pass
+            self._plan = None
 
     # ---- fused product + all-gather over peer memory ------------------------------------------------
     def _setup_arenas(self, comm):
@@ -91,9 +114,13 @@ class MPIFredholm1(MPILinearOperator):
         off = int(self.islstart[rank]) * pout * esz
         others = [peers[r] + off for r in range(comm.Get_size()) if r != rank]
         arr = (C.c_void_p * len(others))(*others)
-        _lib.check(_lib.lib.b2_batched_gemm_allgather(_lib.ctx(), self.G.data_ptr(), xs.data_ptr(), base + off, arr,
-                                                      len(others), self.nsl, self.nx, self.ny, self.nz, int(adjoint),
-                                                      _lib.code(self._tdtype), _lib.stream()), "b2_batched_gemm_allgather")
+        if self._plan is not None:
+            _lib.check(_lib.lib.b2_fredholm_apply(self._plan, xs.data_ptr(), base + off, arr, len(others), int(adjoint),
+                                                  _lib.stream()), "b2_fredholm_apply")
+        else:
+            _lib.check(_lib.lib.b2_batched_gemm_allgather(_lib.ctx(), self.G.data_ptr(), xs.data_ptr(), base + off, arr,
+                                                          len(others), self.nsl, self.nx, self.ny, self.nz, int(adjoint),
+                                                          _lib.code(self._tdtype), _lib.stream()), "b2_batched_gemm_allgather")
         # stream-ordered cross-rank completion: when this tiny Allreduce finishes every rank's product
         # kernel (and its peer stores) has finished
         allreduce_(comm, self._flag, "sum")
@@ -127,6 +154,12 @@ class MPIFredholm1(MPILinearOperator):
         def product(s0, s1):
             """slices [s0, s1) of this rank, written straight into their place in the gathered output"""
             if s1 <= s0:
+                return
+            if self._plan is not None:      # whole-rank product on the tensor cores (nchunk == 1)
+                assert s0 == 0 and s1 == self.nsl
+                yout = yflat[self.islstart[rank] * pout:self.islend[rank] * pout]
+                _lib.check(_lib.lib.b2_fredholm_apply(self._plan, xs.data_ptr(), yout.data_ptr(), None, 0, int(adjoint),
+                                                      _lib.stream()), "b2_fredholm_apply")
                 return
             G = self.G[s0:s1]
             xin = xs[s0 * per:s1 * per]
