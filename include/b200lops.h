@@ -128,6 +128,20 @@ int b2_second_derivative_halo(int kind, int edge, int adjoint, int* need_lo, int
 int b2_derivative_axis(b2_ctx* ctx, const void* x, void* y, size_t n_outer, size_t n_axis, size_t n_inner,
                        int deriv, int kind, int order, int edge, double sampling, int adjoint, int dtype,
                        void* stream);
+/* Peer-memory halo exchange fused INTO the stencil kernel (replaces the add_ghost_cells Send/Recv pairs of
+ * DistributedArray.py:876-953 as used by FirstDerivative.py:221-247, 276-319 and SecondDerivative.py): every rank
+ * owns a box of b2_halo_bytes(cap) bytes in IPC-mapped memory (b2_symm_alloc + b2_ipc_*); boxes_host[r] is rank r's
+ * box as mapped in this process.  b2_derivative_peer is ONE launch per apply: the first CTAs push the boundary rows
+ * into the neighbours' boxes over NVLink and publish a flag, the CTAs of the first / last row chunk run last and
+ * wait for it.  Collective: same call sequence on every rank of the handle, all on one stream; each rank must
+ * own >= 2 rows; 2 * ncols * sizeof(dtype) must fit in cap_bytes.  deriv = 1 | 2 (first | second derivative). */
+typedef struct b2_halo b2_halo;
+size_t b2_halo_bytes(size_t cap_bytes);
+int b2_halo_create(int rank, int size, void* const* boxes_host, size_t cap_bytes, b2_halo** out);
+int b2_halo_destroy(b2_halo* h);
+int b2_derivative_peer(b2_ctx* ctx, b2_halo* h, const void* x, void* y, size_t nrows_local, size_t ncols,
+                       size_t row0, size_t nrows_global, int deriv, int kind, int order, int edge, double sampling,
+                       int adjoint, int dtype, void* stream);
 /* Same operator on HOST buffers (pageable or pinned).  x_host / y_host address the
  * GLOBAL [nrows_global x ncols] arrays (to_dist keeps the global array replicated on
  * every rank's host, DistributedArray.py:440-459); this call processes rows

@@ -41,12 +41,20 @@ def allreduce_(comm: Comm, buf: torch.Tensor, op: str = SUM) -> torch.Tensor:
                        "b2_peer_allreduce")
             return buf
     if op in (SUM, None) and buf.dtype in (torch.float32, torch.float64) and \
-            buf.numel() * buf.element_size() <= _PEER_VEC_MAX and buf.data_ptr() % 16 == 0:
-        # latency regime (e.g. MPIVStack adjoint with a small model): one-shot all-reduce over peer memory
+            buf.numel() * buf.element_size() <= _PEER_VEC_MAX:
+        # latency regime (e.g. MPIVStack adjoint with a small model): one-shot all-reduce over peer memory.
+        # The transport is chosen from RANK-INVARIANT data only (dtype, element count, op): a rank-local
+        # property such as pointer alignment could send ranks down different paths (and the lazy, collective
+        # mailbox setup) and hang the job; a mis-aligned view is staged through an aligned scratch instead.
+        # The mailbox handles keep a host-side sequence number: all calls on one communicator must be issued
+        # on ONE stream (the current torch stream of the solver loop).
         pv = comm.peer_vec
         if pv is not None:
-            _lib.check(_lib.lib.b2_peer_vec_allreduce(pv, buf.data_ptr(), buf.numel(), _lib.code(buf.dtype),
+            work = buf if buf.data_ptr() % 16 == 0 else buf.clone()
+            _lib.check(_lib.lib.b2_peer_vec_allreduce(pv, work.data_ptr(), work.numel(), _lib.code(work.dtype),
                                                       _lib.stream()), "b2_peer_vec_allreduce")
+            if work is not buf:
+                buf.copy_(work)
             return buf
     _lib.check(_lib.lib.b2_allreduce(comm.nccl, buf.data_ptr(), buf.data_ptr(), buf.numel(),
                                      _lib.code(buf.dtype), _OPS[op], _lib.stream()), "b2_allreduce")

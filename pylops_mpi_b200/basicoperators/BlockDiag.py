@@ -11,6 +11,7 @@ import torch
 from ..comm import COMM_WORLD, resolve
 from ..DistributedArray import DistributedArray
 from ..LinearOperator import MPILinearOperator, _get_dtype
+from ..local import apply_into
 from ..utils.decorators import reshaped
 
 
@@ -18,11 +19,7 @@ def _apply_ops(ops, x: torch.Tensor, bounds, out: torch.Tensor, out_bounds, adjo
     for iop, oper in enumerate(ops):
         xi = x[bounds[iop]:bounds[iop + 1]]
         oi = out[out_bounds[iop]:out_bounds[iop + 1]]
-        fn = oper.rmatvec if adjoint else oper.matvec
-        try:
-            fn(xi, out=oi)                     # b200 local ops write in place
-        except TypeError:
-            oi.copy_(fn(xi))
+        apply_into(oper, xi, oi, adjoint)      # b200 local ops write in place (dtype-checked), others via a temp
 
 
 class MPIBlockDiag(MPILinearOperator):

@@ -59,6 +59,8 @@ class MPIFirstDerivative(MPILinearOperator):
                                                      C.byref(need_lo), C.byref(need_hi)), "b2_first_derivative_halo")
         return need_lo.value, need_hi.value
 
+    _deriv = 1      # MPISecondDerivative: 2 (same fused peer-halo entry point)
+
     def _kernel(self, ctx, xp, yp, lop, lo_n, hip, hi_n, nrows, ncols, row0, adjoint, code):
         _lib.check(_lib.lib.b2_first_derivative(ctx, xp, yp, lop, lo_n, hip, hi_n, nrows, ncols, row0, self.dims[0],
                                                 self._kind_code, self.order, int(self.edge), float(self.sampling),
@@ -122,6 +124,21 @@ class MPIFirstDerivative(MPILinearOperator):
         if x.size == 1:
             launch(0, nloc, None, 0, None, 0)
             return y
+        # fused path: halo rows are pushed / awaited INSIDE the stencil kernel over NVLink peer memory (ONE launch,
+        # no NCCL, no side stream).  The choice uses rank-invariant data only (global row split, dtype, ncols).
+        esz = 4 if real_dt is torch.float32 else 8
+        vec = 16 // esz
+        if min(rows) >= max(nl, nh, 1) and ncols % vec == 0 and ncols // vec >= 8 and \
+                2 * ncols * esz <= x.base_comm.HALO_CAP and x.base_comm.size == x.size and x.mask is None:
+            halo = x.base_comm.halo
+            if halo is not None:
+                if xr.data_ptr() % 16:        # never branch on a rank-local property: stage a mis-aligned view
+                    xr = xr.clone()
+                _lib.check(_lib.lib.b2_derivative_peer(ctx, halo, xr.data_ptr(), yr.data_ptr(), nloc, ncols, row0,
+                                                       self.dims[0], self._deriv, self._kind_code, self.order,
+                                                       int(self.edge), float(self.sampling), int(adjoint), code,
+                                                       _lib.stream()), "b2_derivative_peer")
+                return y
         n_lo, n_hi = plan["recv_lo"], plan["recv_hi"]
         lo = torch.empty((n_lo, ncols), dtype=real_dt, device=xl.device) if n_lo else None
         hi = torch.empty((n_hi, ncols), dtype=real_dt, device=xl.device) if n_hi else None

@@ -14,6 +14,8 @@ from .FirstDerivative import MPIFirstDerivative, _KINDS
 
 
 class MPISecondDerivative(MPIFirstDerivative):
+    _deriv = 2
+
     def __init__(self, dims, sampling: float = 1.0, kind: str = "centered", edge: bool = False,
                  base_comm=COMM_WORLD, dtype=np.float64):
         if kind not in _KINDS:

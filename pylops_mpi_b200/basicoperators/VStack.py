@@ -12,6 +12,7 @@ from ..comm import COMM_WORLD, resolve, SUM
 from ..Distributed import allreduce_
 from ..DistributedArray import DistributedArray, Partition
 from ..LinearOperator import MPILinearOperator, _get_dtype
+from ..local import apply_into
 from ..utils.decorators import reshaped
 
 
@@ -42,10 +43,7 @@ class MPIVStack(MPILinearOperator):
                              local_shapes=self.local_shapes_n, dtype=self.dtype)
         for iop, oper in enumerate(self.ops):
             oi = y.local_array[self.nnops[iop]:self.nnops[iop + 1]]
-            try:
-                oper.matvec(x.local_array, out=oi)
-            except TypeError:
-                oi.copy_(oper.matvec(x.local_array))
+            apply_into(oper, x.local_array, oi, False)
         return y
 
     @reshaped(forward=False, stacking=True)
@@ -57,13 +55,14 @@ class MPIVStack(MPILinearOperator):
         for iop, oper in enumerate(self.ops):
             xi = x.local_array[self.nnops[iop]:self.nnops[iop + 1]]
             if iop == 0:
-                try:
-                    oper.rmatvec(xi, out=acc)
-                except TypeError:
-                    acc.copy_(oper.rmatvec(xi))
+                apply_into(oper, xi, acc, True)
             else:
                 tmp = oper.rmatvec(xi)
-                y._lincomb(1.0, tmp, 1.0, acc, out=acc)
+                if tmp.dtype != acc.dtype:        # mixed-dtype stack: accumulate in the operator's result dtype
+                    if tmp.dtype.is_complex and not acc.dtype.is_complex:
+                        raise TypeError(f"cannot accumulate {tmp.dtype} into a {acc.dtype} model")
+                    tmp = tmp.to(acc.dtype)
+                y._lincomb(1.0, tmp.reshape(-1).contiguous(), 1.0, acc, out=acc)
         if len(self.ops) == 0:
             acc.zero_()
         allreduce_(x.base_comm, acc, SUM)

@@ -124,7 +124,7 @@ class Comm:
             self._nccl = h
         return self._nccl
 
-    def _ipc_mailboxes(self, attr: str, nbytes_fn: str, create_fn: str):
+    def _ipc_mailboxes(self, attr: str, nbytes_fn, create_fn):
         """collective lazy setup of an IPC-mapped mailbox group (one symmetric buffer per rank, every
         rank maps every peer's); returns the library handle or None when CUDA IPC is unavailable"""
         if self._size == 1 or self._size > 8 or os.environ.get("B2_PEER_ALLREDUCE", "1") == "0":
@@ -133,7 +133,7 @@ class Comm:
             from . import _lib
             ok, ptr, mine, hnd = 1, C.c_void_p(), b"", None
             try:
-                nbytes = getattr(_lib.lib, nbytes_fn)()
+                nbytes = getattr(_lib.lib, nbytes_fn)() if isinstance(nbytes_fn, str) else nbytes_fn()
                 _lib.check(_lib.lib.b2_symm_alloc(nbytes, C.byref(ptr)), "b2_symm_alloc")
                 h = (C.c_char * 64)()
                 _lib.check(_lib.lib.b2_ipc_get_handle(ptr, h), "b2_ipc_get_handle")
@@ -153,7 +153,10 @@ class Comm:
                                        "b2_ipc_open_handle")
                             boxes[r] = q.value
                     hnd = C.c_void_p()
-                    _lib.check(getattr(_lib.lib, create_fn)(self._rank, self._size, boxes, C.byref(hnd)), create_fn)
+                    if isinstance(create_fn, str):
+                        _lib.check(getattr(_lib.lib, create_fn)(self._rank, self._size, boxes, C.byref(hnd)), create_fn)
+                    else:
+                        create_fn(boxes, hnd)
                 except Exception:
                     ok = 0
             else:
@@ -173,6 +176,21 @@ class Comm:
     def peer_vec(self):
         """b2_peer_vec handle: mailboxes for one-shot small-VECTOR all-reduces over peer memory"""
         return self._ipc_mailboxes("_peer_vec", "b2_peer_vec_bytes", "b2_peer_vec_create")
+
+    HALO_CAP = int(os.environ.get("B2_HALO_CAP_BYTES", 4 << 20))   # bytes per (parity, side) slot of a halo box
+
+    @property
+    def halo(self):
+        """b2_halo handle: per-rank boxes for the halo rows the stencil kernels exchange over NVLink peer
+        memory INSIDE the kernel (one launch per apply, no NCCL); None when CUDA IPC is unavailable"""
+        if os.environ.get("B2_PEER_HALO", "1") == "0":
+            return None
+        from . import _lib
+        cap = self.HALO_CAP
+
+        def create(boxes, hnd):
+            _lib.check(_lib.lib.b2_halo_create(self._rank, self._size, boxes, cap, C.byref(hnd)), "b2_halo_create")
+        return self._ipc_mailboxes("_halo", lambda: _lib.lib.b2_halo_bytes(cap), create)
 
     def split_by_mask(self, mask: Sequence[int]) -> "Comm":
         """cached ``Split(color=mask[rank], key=rank)`` (DistributedArray.py:74-100)"""

@@ -20,6 +20,13 @@
 //      X'[2k+1,2z] = -im x[k,z]   X'[2k+1,2z+1] = re x[k,z]
 // A X' (nx x 2nz) IS the interleaved complex64 result.  Same flops as the complex product (8 nx ny nz).
 //
+// Second operand format, "fp16x2" (B2_FREDHOLM_MODE=h2, default): v*2^e = hi + lo*2^-11 with fp16 hi = rn(v 2^e),
+// lo = rn((v 2^e - hi) 2^11) (22 significant bits; e = power-of-two scale per G slice / per 32-column strip of
+// x so that the largest element sits just below 2^15 -- undone exactly in the epilogue), and
+//   a*b ~= hi_a hi_b + (hi_a lo_b + lo_a hi_b) 2^-11                  (dropped term <= 2^-22 |a||b|)
+// is THREE products on two planes per operand: half the tensor-pipe time, 2/3 of the bytes of bf16x3
+// (A planes = the 4 bytes/element of the float32 original).  Error-compensated split GEMM after Ootomo & Yokota.
+//
 // Operator state vs per-apply data: G is operator state -> its planes (and those of G^H, the reference's
 // `saveGt`) are split ONCE at plan creation; x changes every apply -> `pack_x_kernel` builds the three
 // bf16 planes of X'^T (K-major, so both MMA operands are the canonical "TN" form) right before the product.
@@ -30,6 +37,7 @@
 // Fredholm1.py:131-132 -- the same 16-byte stores into every peer GPU's IPC-mapped output over NVLink).
 #include <stdlib.h>
 #include <string.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -37,16 +45,22 @@ using namespace tcptx;
 
 namespace {
 
-constexpr uint32_t BM = 128, BN = 128, UMMA_K = 16, NPL = 3;
+constexpr uint32_t BM = 128, BN = 128, UMMA_K = 16;
 constexpr uint32_t NUM_THREADS = 192;
 constexpr uint32_t TMEM_COLS = 512;   // 2 accumulator stages x (main | small-terms) x 128 fp32 columns
 constexpr uint32_t ACC_COLS = 2 * BN; // columns of one accumulator stage
+constexpr int MODE_B3 = 0, MODE_H2 = 1;
+constexpr uint32_t ZSTRIP = 32;       // columns of x per pack block / per fp16 scale
 
-template <uint32_t BK>
+__host__ __device__ constexpr uint32_t npl_of(int mode) { return mode == MODE_B3 ? 3u : 2u; }
+
+template <int MODE, uint32_t BK>
 struct Cfg {
-  static constexpr uint32_t TILE_BYTES = 128 * BK * 2;             // one plane tile (128 rows x BK bf16)
-  static constexpr uint32_t STAGE_BYTES = 2 * NPL * TILE_BYTES;     // A0..A2, B0..B2
-  static constexpr uint32_t STAGES = (BK == 64) ? 2 : 4;            // 192 KB of operand ring either way
+  static constexpr uint32_t NPL = npl_of(MODE);
+  static constexpr uint32_t NQ = MODE == MODE_B3 ? 6 : 3;           // tensor-core products per k-step
+  static constexpr uint32_t TILE_BYTES = 128 * BK * 2;             // one plane tile (128 rows x BK 16-bit)
+  static constexpr uint32_t STAGE_BYTES = 2 * NPL * TILE_BYTES;     // A planes, B planes
+  static constexpr uint32_t STAGES = (192u * 1024u) / STAGE_BYTES;  // 192 KB operand ring: 2/4 (b3), 3/6 (h2)
   static constexpr uint32_t SBO = 8 * BK * 2;                       // 8 rows of one swizzle span
   static constexpr uint64_t LAYOUT = (BK == 64) ? 2 : 4;            // SWIZZLE_128B : SWIZZLE_64B
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
@@ -57,12 +71,22 @@ struct PeerOut {
   int n;
 };
 
-template <uint32_t BK>
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// kind::f16 instruction descriptor, both operands K-major; fmt: 1 = bf16, 0 = fp16
+__device__ __forceinline__ uint32_t make_idesc(uint32_t M, uint32_t N, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+template <int MODE, uint32_t BK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fredholm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   float* __restrict__ Y, const PeerOut peers, uint32_t nsl, uint32_t m, uint32_t n, uint32_t kpad,
-                   uint32_t n_umma, int vec_ok) {
-  using C = Cfg<BK>;
+                   float* __restrict__ Y, const PeerOut peers, const float* __restrict__ invA,
+                   const float* __restrict__ invB, uint32_t nstrips, uint32_t strip_cols, uint32_t nsl, uint32_t m,
+                   uint32_t n, uint32_t kpad, uint32_t n_umma, int vec_ok) {
+  using C = Cfg<MODE, BK>;
+  constexpr uint32_t NPL = C::NPL;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -101,6 +125,7 @@ fredholm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      bool dep_ready = false;     // the B planes are written by the pack kernel launched just before (PDL)
       const uint32_t tx_bytes = NPL * (BM * BK * 2) + NPL * (n_umma * BK * 2);
       for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const uint32_t n_blk = tile % num_n, m_blk = (tile / num_n) % num_m, s = tile / (num_n * num_m);
@@ -110,9 +135,10 @@ fredholm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           uint8_t* sb = sa + NPL * C::TILE_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
 #pragma unroll
-          for (uint32_t p = 0; p < NPL; ++p)
+          for (uint32_t p = 0; p < NPL; ++p)      // operator state: independent of the pack kernel
             tma_load_3d(sa + p * C::TILE_BYTES, &tmA, &full_bar[stage], (int32_t)(kb * BK), (int32_t)(m_blk * BM),
                         (int32_t)(s * NPL + p));
+          if (!dep_ready) { grid_dep_wait(); dep_ready = true; }
 #pragma unroll
           for (uint32_t p = 0; p < NPL; ++p)
             tma_load_3d(sb + p * C::TILE_BYTES, &tmB, &full_bar[stage], (int32_t)(kb * BK), (int32_t)(n_blk * BN),
@@ -124,9 +150,12 @@ fredholm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(BM, n_umma, false, false);   // both operands K-major
-      // small terms first: (A2,B0) (A1,B1) (A0,B2) (A1,B0) (A0,B1) (A0,B0)
-      const uint32_t pa[6] = {2, 1, 0, 1, 0, 0}, pb[6] = {0, 1, 2, 0, 1, 0};
+      const uint32_t idesc = make_idesc(BM, n_umma, MODE == MODE_B3 ? 1u : 0u);
+      // small terms first; the LAST product of the list is the leading term (main accumulator)
+      //   b3: (A2,B0) (A1,B1) (A0,B2) (A1,B0) (A0,B1) | (A0,B0)      h2: (hi,lo) (lo,hi) | (hi,hi)
+      constexpr uint32_t NQ = C::NQ;
+      const uint32_t pa[6] = {MODE == MODE_B3 ? 2u : 0u, 1u, 0u, 1u, 0u, 0u};
+      const uint32_t pb[6] = {MODE == MODE_B3 ? 0u : 1u, MODE == MODE_B3 ? 1u : 0u, MODE == MODE_B3 ? 2u : 0u, 0u, 1u, 0u};
       uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -140,11 +169,11 @@ fredholm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
           for (uint32_t kk = 0; kk < BK / UMMA_K; ++kk) {
 #pragma unroll
-            for (uint32_t q = 0; q < 6; ++q) {
+            for (uint32_t q = 0; q < NQ; ++q) {
               // K-major, swizzled: 8-row groups SBO apart, k advances 32 B inside the swizzle span
               const uint64_t adesc = make_smem_desc(sa + pa[q] * C::TILE_BYTES + kk * UMMA_K * 2, 0, C::SBO, C::LAYOUT);
               const uint64_t bdesc = make_smem_desc(sb + pb[q] * C::TILE_BYTES + kk * UMMA_K * 2, 0, C::SBO, C::LAYOUT);
-              if (q == 5) umma_bf16(tmem_main, adesc, bdesc, idesc, (kb | kk) != 0 ? 1u : 0u);
+              if (q == NQ - 1) umma_bf16(tmem_main, adesc, bdesc, idesc, (kb | kk) != 0 ? 1u : 0u);
               else umma_bf16(tmem_small, adesc, bdesc, idesc, (kb | kk | q) != 0 ? 1u : 0u);
             }
           }
@@ -159,21 +188,32 @@ fredholm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // ===================== epilogue: TMEM -> registers -> y (+ peers over NVLink) =====================
     const uint32_t g = warp & 3;
     uint32_t acc = 0, acc_phase = 0;
+    grid_dep_wait();     // y (and, in h2 mode, the scales of x) may only be touched once the previous kernel is done
     for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const uint32_t n_blk = tile % num_n, m_blk = (tile / num_n) % num_m, s = tile / (num_n * num_m);
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t row = m_blk * BM + g * 32 + lane;
       const size_t roff = ((size_t)s * m + row) * n;
+      const float sa_inv = MODE == MODE_H2 ? invA[s] : 1.f;
 #pragma unroll 1
       for (uint32_t c0 = 0; c0 < n_umma; c0 += 32) {
         uint32_t v[32], w[32];
         tmem_ld_32x32b_x32(tmem_base + ((g * 32u) << 16) + acc * ACC_COLS + c0, v);
         tmem_ld_32x32b_x32(tmem_base + ((g * 32u) << 16) + acc * ACC_COLS + BN + c0, w);
         tmem_ld_wait();
-#pragma unroll
-        for (uint32_t j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
         const uint32_t col0 = n_blk * BN + c0;
+        if (MODE == MODE_H2) {
+          // undo the power-of-two operand scales (exact) and the 2^11 of the correction terms
+          const uint32_t strip = col0 / strip_cols;
+          const float sc = sa_inv * (strip < nstrips ? invB[(size_t)s * nstrips + strip] : 0.f);
+#pragma unroll
+          for (uint32_t j = 0; j < 32; ++j)
+            v[j] = __float_as_uint(fmaf(__uint_as_float(w[j]), 1.f / 2048.f, __uint_as_float(v[j])) * sc);
+        } else {
+#pragma unroll
+          for (uint32_t j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+        }
         if (row < m && col0 < n) {
           const size_t off = roff + col0;
           if (vec_ok && col0 + 32 <= n) {
@@ -210,25 +250,69 @@ fredholm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   }
 }
 
-// ---- bf16x3 split --------------------------------------------------------------------------------------
-struct Split3 {
-  __nv_bfloat16 p[3];
-};
-__device__ __forceinline__ Split3 split3(float v) {
-  Split3 r;
-  r.p[0] = __float2bfloat16_rn(v);
-  const float r1 = v - __bfloat162float(r.p[0]);
-  r.p[1] = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(r.p[1]);
-  r.p[2] = __float2bfloat16_rn(r2);
+// ---- operand splits (16-bit planes stored as raw ushort) ---------------------------------------------------
+template <int MODE> struct Split { unsigned short p[npl_of(MODE)]; };
+
+template <int MODE>
+__device__ __forceinline__ Split<MODE> split(float v, float scale) {
+  Split<MODE> r;
+  if (MODE == MODE_B3) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v);
+    const float r1 = v - __bfloat162float(h0);
+    const __nv_bfloat16 h1 = __float2bfloat16_rn(r1);
+    const float r2 = r1 - __bfloat162float(h1);
+    r.p[0] = __bfloat16_as_ushort(h0);
+    r.p[1] = __bfloat16_as_ushort(h1);
+    r.p[npl_of(MODE) - 1] = __bfloat16_as_ushort(__float2bfloat16_rn(r2));
+  } else {
+    const float vs = v * scale;                      // |vs| < 2^15: no fp16 overflow
+    const __half h0 = __float2half_rn(vs);
+    r.p[0] = __half_as_ushort(h0);
+    r.p[1] = __half_as_ushort(__float2half_rn((vs - __half2float(h0)) * 2048.f));
+  }
   return r;
+}
+__device__ __forceinline__ unsigned short neg16(unsigned short h) { return h ^ 0x8000u; }   // bf16 and fp16: sign bit
+
+// power-of-two scale that puts amax just below 2^15 (exponent clamped so scale and 1/scale stay normal floats)
+__device__ __forceinline__ void pow2_scale(float amax, float* scale, float* inv) {
+  int ex = 0;
+  if (amax > 0.f && amax < INFINITY) frexpf(amax, &ex);      // amax = f * 2^ex, f in [0.5, 1)
+  else ex = 15;
+  int e = 15 - ex;
+  e = e > 100 ? 100 : (e < -100 ? -100 : e);
+  *scale = ldexpf(1.f, e);
+  *inv = ldexpf(1.f, -e);
+}
+
+__device__ __forceinline__ float block_max(float v, float* red) {
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < nw; ++i) r = fmaxf(r, red[i]);
+  __syncthreads();
+  return r;
+}
+
+// h2 only: scale of each G slice (operator state, once per plan)
+__global__ void __launch_bounds__(256) slice_scale_kernel(const float* __restrict__ G, size_t per_slice, float* scA, float* invA) {
+  __shared__ float red[8];
+  const float* g = G + (size_t)blockIdx.x * per_slice;
+  float am = 0.f;
+  for (size_t i = threadIdx.x; i < per_slice; i += blockDim.x) am = fmaxf(am, fabsf(g[i]));
+  am = block_max(am, red);
+  if (threadIdx.x == 0) pow2_scale(am, &scA[blockIdx.x], &invA[blockIdx.x]);
 }
 
 // operator state, once per plan: planes[s][p][r][c'] (c' < kpad, zero padded) of op(G[s]) as a real matrix.
 //   dir 0:  r = i (nx rows),  c' = cx ? 2j+cc : j   <- G[s][i][j]            (cc: 0 = re, 1 = im)
 //   dir 1:  r = j (ny rows),  c' = cx ? 2i+cc : i   <- conj(G[s][i][j])      (G^H)
-__global__ void pack_g_kernel(const float* __restrict__ G, __nv_bfloat16* __restrict__ out, size_t nsl, size_t nx,
-                              size_t ny, int cx, int dir, size_t rows, size_t kpad) {
+template <int MODE>
+__global__ void pack_g_kernel(const float* __restrict__ G, unsigned short* __restrict__ out, const float* __restrict__ scA,
+                              size_t nsl, size_t nx, size_t ny, int cx, int dir, size_t rows, size_t kpad) {
+  constexpr uint32_t NPL = npl_of(MODE);
   const size_t total = nsl * rows * kpad;
   const size_t kp = (dir == 0 ? ny : nx) * (cx ? 2 : 1);
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -242,62 +326,97 @@ __global__ void pack_g_kernel(const float* __restrict__ G, __nv_bfloat16* __rest
       v = cx ? G[2 * idx + cc] : G[idx];
       if (dir == 1 && cc == 1) v = -v;
     }
-    const Split3 sp = split3(v);
+    const Split<MODE> sp = split<MODE>(v, MODE == MODE_H2 ? scA[s] : 1.f);
     const size_t base = ((s * NPL) * rows + r) * kpad + c;
 #pragma unroll
-    for (int p = 0; p < 3; ++p) out[base + (size_t)p * rows * kpad] = sp.p[p];
+    for (uint32_t p = 0; p < NPL; ++p) out[base + (size_t)p * rows * kpad] = sp.p[p];
   }
 }
 
-// per apply: planes of X'^T,  BT[s][p][n'][k'] (k' < kp; padding columns stay zero from plan creation)
+// per apply: planes of X'^T,  BT[s][p][n'][k'] (k' < kpad; columns in [kp, kpad) are written as zeros)
 //   complex: n' = 2z+d, k' = 2k+c:  (c,d) = (0,0) re, (1,0) -im, (0,1) im, (1,1) re
 //   real   : n' = z,    k' = k
-template <bool CX>
+// One block per (32-column strip of x, slice): h2 first takes the strip's amax (power-of-two scale, its inverse
+// goes to invB for the epilogue), then 32 x 32 tiles are transposed through shared memory and written as
+// 16-byte (complex) / 8-byte (real) vectors along k'.
+template <bool CX, int MODE>
 __global__ void __launch_bounds__(256)
-pack_x_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ BT, uint32_t K, uint32_t nz, uint32_t nrows,
-              uint32_t kpad) {
+pack_x_kernel(const float* __restrict__ x, unsigned short* __restrict__ BT, float* __restrict__ invB, uint32_t K,
+              uint32_t nz, uint32_t nrows, uint32_t kpad) {
+  constexpr uint32_t NPL = npl_of(MODE);
   __shared__ float2 tile[32][33];
-  const uint32_t s = blockIdx.z, k0 = blockIdx.y * 32, z0 = blockIdx.x * 32;
+  __shared__ float red[8];
+  grid_dep_launch();               // PDL: the product kernel may start its prologue / A loads now
+  const uint32_t s = blockIdx.y, z0 = blockIdx.x * ZSTRIP;
   const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (uint32_t kk = ty; kk < 32; kk += 8) {
-    const uint32_t k = k0 + kk, z = z0 + tx;
-    float2 v = make_float2(0.f, 0.f);
-    if (k < K && z < nz) {
-      const size_t idx = ((size_t)s * K + k) * nz + z;
-      if (CX) v = reinterpret_cast<const float2*>(x)[idx];
-      else v.x = x[idx];
-    }
-    tile[kk][tx] = v;
-  }
-  __syncthreads();
-  const size_t plane = (size_t)nrows * kpad;
-  __nv_bfloat16* base = BT + (size_t)s * NPL * plane;
-  const uint32_t k = k0 + tx;
-  for (uint32_t zz = ty; zz < 32; zz += 8) {
-    const uint32_t z = z0 + zz;
-    if (k >= K || z >= nz) continue;
-    const float2 v = tile[tx][zz];
-    const Split3 re = split3(v.x);
-    if (CX) {
-      const Split3 im = split3(v.y);
-#pragma unroll
-      for (int p = 0; p < 3; ++p) {
-        __nv_bfloat162 r0, r1;
-        r0.x = re.p[p];  r0.y = __hneg(im.p[p]);      // row 2z  : k' = 2k -> re, 2k+1 -> -im
-        r1.x = im.p[p];  r1.y = re.p[p];              // row 2z+1: k' = 2k -> im, 2k+1 -> re
-        __nv_bfloat16* q = base + p * plane;
-        *reinterpret_cast<__nv_bfloat162*>(q + (size_t)(2 * z) * kpad + 2 * k) = r0;
-        *reinterpret_cast<__nv_bfloat162*>(q + (size_t)(2 * z + 1) * kpad + 2 * k) = r1;
+  const float* xs = x + (size_t)s * K * nz * (CX ? 2 : 1);
+  float scale = 1.f;
+  if (MODE == MODE_H2) {
+    float am = 0.f;
+    const uint32_t z = z0 + tx;
+    if (z < nz)
+      for (uint32_t k = ty; k < K; k += 8) {
+        if (CX) {
+          const float2 v = reinterpret_cast<const float2*>(xs)[(size_t)k * nz + z];
+          am = fmaxf(am, fmaxf(fabsf(v.x), fabsf(v.y)));
+        } else {
+          am = fmaxf(am, fabsf(xs[(size_t)k * nz + z]));
+        }
       }
-    } else {
-#pragma unroll
-      for (int p = 0; p < 3; ++p) base[p * plane + (size_t)z * kpad + k] = re.p[p];
+    am = block_max(am, red);
+    float inv;
+    pow2_scale(am, &scale, &inv);
+    if (threadIdx.x == 0) invB[(size_t)s * gridDim.x + blockIdx.x] = inv;
+  }
+  const size_t plane = (size_t)nrows * kpad;
+  unsigned short* base = BT + (size_t)s * NPL * plane;
+  const uint32_t zz = threadIdx.x >> 3, kq = threadIdx.x & 7;     // write phase: one z, four consecutive k
+  const uint32_t kspan = (kpad / (CX ? 2 : 1) + 31) / 32 * 32;    // cover the padding columns too
+  for (uint32_t k0 = 0; k0 < kspan; k0 += 32) {
+    for (uint32_t kk = ty; kk < 32; kk += 8) {
+      const uint32_t k = k0 + kk, z = z0 + tx;
+      float2 v = make_float2(0.f, 0.f);
+      if (k < K && z < nz) {
+        if (CX) v = reinterpret_cast<const float2*>(xs)[(size_t)k * nz + z];
+        else v.x = xs[(size_t)k * nz + z];
+      }
+      tile[kk][tx] = v;
     }
+    __syncthreads();
+    const uint32_t z = z0 + zz, kb = k0 + 4 * kq;
+    if (z < nz && kb * (CX ? 2 : 1) < kpad) {
+      Split<MODE> re[4], im[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 v = tile[4 * kq + j][zz];
+        re[j] = split<MODE>(v.x, scale);
+        if (CX) im[j] = split<MODE>(v.y, scale);
+      }
+#pragma unroll
+      for (uint32_t p = 0; p < NPL; ++p) {
+        unsigned short* q = base + p * plane;
+        if (CX) {
+          uint4 r0, r1;      // row 2z: (re, -im) pairs; row 2z+1: (im, re) pairs
+          r0.x = re[0].p[p] | ((uint32_t)neg16(im[0].p[p]) << 16);  r1.x = im[0].p[p] | ((uint32_t)re[0].p[p] << 16);
+          r0.y = re[1].p[p] | ((uint32_t)neg16(im[1].p[p]) << 16);  r1.y = im[1].p[p] | ((uint32_t)re[1].p[p] << 16);
+          r0.z = re[2].p[p] | ((uint32_t)neg16(im[2].p[p]) << 16);  r1.z = im[2].p[p] | ((uint32_t)re[2].p[p] << 16);
+          r0.w = re[3].p[p] | ((uint32_t)neg16(im[3].p[p]) << 16);  r1.w = im[3].p[p] | ((uint32_t)re[3].p[p] << 16);
+          *reinterpret_cast<uint4*>(q + (size_t)(2 * z) * kpad + 2 * kb) = r0;
+          *reinterpret_cast<uint4*>(q + (size_t)(2 * z + 1) * kpad + 2 * kb) = r1;
+        } else {
+          uint2 r0;
+          r0.x = re[0].p[p] | ((uint32_t)re[1].p[p] << 16);
+          r0.y = re[2].p[p] | ((uint32_t)re[3].p[p] << 16);
+          *reinterpret_cast<uint2*>(q + (size_t)z * kpad + kb) = r0;
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
 int make_tmap3(CUtensorMap* tm, const void* base, uint64_t kpad, uint64_t rows, uint64_t nmat, uint32_t box_k,
-               uint32_t box_rows) {
+               uint32_t box_rows, bool fp16) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return B2_ERR_UNSUPPORTED;
   cuuint64_t gdim[3] = {kpad, rows, nmat};
@@ -305,8 +424,9 @@ int make_tmap3(CUtensorMap* tm, const void* base, uint64_t kpad, uint64_t rows, 
   cuuint32_t box[3] = {box_k, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   const CUtensorMapSwizzle sw = box_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(tm, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base),
+                  gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? B2_OK : B2_ERR_ARG;
 }
 
@@ -318,12 +438,14 @@ struct b2_fredholm_plan {
   b2_ctx* ctx;
   size_t nsl, nx, ny, nz;
   int cx;                       // complex64 (1) or float32 (0)
-  uint32_t bk;                  // 64 (128B swizzle, 2 stages) or 32 (64B swizzle, 4 stages)
+  int mode;                     // MODE_B3 (bf16x3) or MODE_H2 (fp16x2)
+  uint32_t bk;                  // 64 (128B swizzle) or 32 (64B swizzle, twice the stages)
   // per direction d (0 forward, 1 adjoint): output rows m[d], contraction length kp[d] (real), padded kpad[d]
   size_t m[2], kp[2], kpad[2];
-  __nv_bfloat16* A[2];          // planes of op(G): [nsl][3][m][kpad]
-  __nv_bfloat16* BT[2];         // planes of X'^T : [nsl][3][n][kpad]   (per-apply workspace, padding kept zero)
-  uint32_t n, n_umma;           // output columns (real), UMMA N
+  unsigned short* A[2];         // planes of op(G): [nsl][npl][m][kpad]
+  unsigned short* BT[2];        // planes of X'^T : [nsl][npl][n][kpad]   (per-apply workspace)
+  float *scA, *invA, *invB;     // h2: per-slice scale of G (and inverse), inverse scale per (slice, x strip)
+  uint32_t n, n_umma, nstrips;  // output columns (real), UMMA N, 32-column strips of x
   CUtensorMap tmA[2], tmB[2];
 };
 
@@ -333,6 +455,9 @@ extern "C" int b2_fredholm_plan_destroy(b2_fredholm_plan* pl) {
     if (pl->A[d]) cudaFree(pl->A[d]);
     if (pl->BT[d]) cudaFree(pl->BT[d]);
   }
+  if (pl->scA) cudaFree(pl->scA);
+  if (pl->invA) cudaFree(pl->invA);
+  if (pl->invB) cudaFree(pl->invB);
   delete pl;
   return B2_OK;
 }
@@ -342,7 +467,7 @@ extern "C" int b2_fredholm_plan_create(b2_ctx* ctx, const void* G, size_t nsl, s
   if (!ctx || !out || !G) return B2_ERR_ARG;
   if (dtype != B2_F32 && dtype != B2_C64) return B2_ERR_DTYPE;
   if (nsl == 0 || nx == 0 || ny == 0 || nz == 0) return B2_ERR_ARG;
-  if (nsl * NPL > 0x7fffffffull || nx > 0x3fffffffull || ny > 0x3fffffffull || nz > 0x3fffffffull) return B2_ERR_ARG;
+  if (nsl * 3 > 0x7fffffffull || nsl > 65535 || nx > 0x3fffffffull || ny > 0x3fffffffull || nz > 0x3fffffffull) return B2_ERR_ARG;
   if (!b2_aligned16(G)) return B2_ERR_ALIGN;
   b2_fredholm_plan* pl = new b2_fredholm_plan();
   memset(pl, 0, sizeof(*pl));
@@ -350,38 +475,51 @@ extern "C" int b2_fredholm_plan_create(b2_ctx* ctx, const void* G, size_t nsl, s
   pl->nsl = nsl; pl->nx = nx; pl->ny = ny; pl->nz = nz;
   pl->cx = dtype == B2_C64;
   {
-    static int bk = -1;
-    if (bk < 0) {
-      const char* e = getenv("B2_FREDHOLM_BK");
-      bk = e ? atoi(e) : 32;
-      if (bk != 32 && bk != 64) bk = 32;
-    }
-    pl->bk = (uint32_t)bk;
+    const char* e = getenv("B2_FREDHOLM_BK");
+    const int bk = e ? atoi(e) : 32;
+    pl->bk = bk == 64 ? 64u : 32u;
+    const char* mo = getenv("B2_FREDHOLM_MODE");
+    pl->mode = (mo && (mo[0] == 'b' || mo[0] == 'B')) ? MODE_B3 : MODE_H2;
   }
+  const uint32_t npl = npl_of(pl->mode);
   const size_t mul = pl->cx ? 2 : 1;
   pl->n = (uint32_t)(nz * mul);
   pl->n_umma = pl->n >= BN ? BN : (uint32_t)round_up(pl->n, 16);
+  pl->nstrips = (uint32_t)((nz + ZSTRIP - 1) / ZSTRIP);
   pl->m[0] = nx; pl->kp[0] = ny * mul;
   pl->m[1] = ny; pl->kp[1] = nx * mul;
   int rc = B2_OK;
+  cudaError_t e = cudaMalloc((void**)&pl->scA, nsl * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&pl->invA, nsl * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&pl->invB, nsl * pl->nstrips * sizeof(float));
+  if (e != cudaSuccess) rc = (int)e;
+  if (rc == B2_OK && pl->mode == MODE_H2) {
+    slice_scale_kernel<<<(unsigned)nsl, 256>>>((const float*)G, nx * ny * mul, pl->scA, pl->invA);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) rc = (int)e;
+  }
   for (int d = 0; d < 2 && rc == B2_OK; ++d) {
     pl->kpad[d] = round_up(pl->kp[d], 8);
-    const size_t a_elems = nsl * NPL * pl->m[d] * pl->kpad[d], b_elems = nsl * NPL * (size_t)pl->n * pl->kpad[d];
-    cudaError_t e = cudaMalloc((void**)&pl->A[d], a_elems * 2);
+    const size_t a_elems = nsl * npl * pl->m[d] * pl->kpad[d], b_elems = nsl * npl * (size_t)pl->n * pl->kpad[d];
+    e = cudaMalloc((void**)&pl->A[d], a_elems * 2);
     if (e == cudaSuccess) e = cudaMalloc((void**)&pl->BT[d], b_elems * 2);
     if (e == cudaSuccess) e = cudaMemset(pl->BT[d], 0, b_elems * 2);
     if (e != cudaSuccess) { rc = (int)e; break; }
     const size_t total = nsl * pl->m[d] * pl->kpad[d];
     size_t blocks = (total + 255) / 256;
     if (blocks > (size_t)ctx->sm_count * 32) blocks = (size_t)ctx->sm_count * 32;
-    pack_g_kernel<<<(unsigned)blocks, 256>>>((const float*)G, pl->A[d], nsl, nx, ny, pl->cx, d, pl->m[d], pl->kpad[d]);
+    if (pl->mode == MODE_B3)
+      pack_g_kernel<MODE_B3><<<(unsigned)blocks, 256>>>((const float*)G, pl->A[d], pl->scA, nsl, nx, ny, pl->cx, d, pl->m[d], pl->kpad[d]);
+    else
+      pack_g_kernel<MODE_H2><<<(unsigned)blocks, 256>>>((const float*)G, pl->A[d], pl->scA, nsl, nx, ny, pl->cx, d, pl->m[d], pl->kpad[d]);
     e = cudaGetLastError();
     if (e != cudaSuccess) { rc = (int)e; break; }
-    rc = make_tmap3(&pl->tmA[d], pl->A[d], pl->kpad[d], pl->m[d], nsl * NPL, pl->bk, BM);
-    if (rc == B2_OK) rc = make_tmap3(&pl->tmB[d], pl->BT[d], pl->kpad[d], pl->n, nsl * NPL, pl->bk, pl->n_umma);
+    const bool fp16 = pl->mode == MODE_H2;
+    rc = make_tmap3(&pl->tmA[d], pl->A[d], pl->kpad[d], pl->m[d], nsl * npl, pl->bk, BM, fp16);
+    if (rc == B2_OK) rc = make_tmap3(&pl->tmB[d], pl->BT[d], pl->kpad[d], pl->n, nsl * npl, pl->bk, pl->n_umma, fp16);
   }
   if (rc == B2_OK) {
-    cudaError_t e = cudaDeviceSynchronize();
+    e = cudaDeviceSynchronize();
     if (e != cudaSuccess) rc = (int)e;
   }
   if (rc != B2_OK) {
@@ -392,11 +530,12 @@ extern "C" int b2_fredholm_plan_create(b2_ctx* ctx, const void* G, size_t nsl, s
   return B2_OK;
 }
 
-template <uint32_t BK>
+template <int MODE, uint32_t BK>
 static int launch_product(b2_fredholm_plan* pl, int d, float* y, const PeerOut& po, cudaStream_t st) {
+  using C = Cfg<MODE, BK>;
   static bool attr_set = false;
   if (!attr_set) {
-    B2_CUDA(cudaFuncSetAttribute(fredholm_tc_kernel<BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<BK>::SMEM_BYTES));
+    B2_CUDA(cudaFuncSetAttribute(fredholm_tc_kernel<MODE, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES));
     attr_set = true;
   }
   const uint32_t m = (uint32_t)pl->m[d];
@@ -405,9 +544,23 @@ static int launch_product(b2_fredholm_plan* pl, int d, float* y, const PeerOut& 
   int vec_ok = (b2_aligned16(y) && (pl->n % 4) == 0) ? 1 : 0;
   for (int i = 0; i < po.n; ++i)
     if (!b2_aligned16(po.p[i])) vec_ok = 0;
-  fredholm_tc_kernel<BK><<<grid, NUM_THREADS, Cfg<BK>::SMEM_BYTES, st>>>(pl->tmA[d], pl->tmB[d], y, po, (uint32_t)pl->nsl, m,
-                                                                        pl->n, (uint32_t)pl->kpad[d], pl->n_umma, vec_ok);
-  B2_LAUNCH_CHECK();
+  // programmatic dependent launch: this kernel's prologue and its loads of the (static) A planes overlap the
+  // tail of the pack kernel; griddepcontrol.wait guards everything that depends on the pack kernel's output
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const uint32_t strip_cols = ZSTRIP * (pl->cx ? 2u : 1u);
+  B2_CUDA(cudaLaunchKernelEx(&cfg, fredholm_tc_kernel<MODE, BK>, pl->tmA[d], pl->tmB[d], y, po, (const float*)pl->invA,
+                             (const float*)pl->invB, pl->nstrips, strip_cols, (uint32_t)pl->nsl, m, pl->n,
+                             (uint32_t)pl->kpad[d], pl->n_umma, vec_ok));
   return B2_OK;
 }
 
@@ -420,15 +573,21 @@ extern "C" int b2_fredholm_apply(b2_fredholm_plan* pl, const void* x, void* y, v
   const int d = adjoint ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   const uint32_t K = (uint32_t)(d == 0 ? pl->ny : pl->nx);
-  dim3 grid((unsigned)((pl->nz + 31) / 32), (unsigned)((K + 31) / 32), (unsigned)pl->nsl);
-  if (grid.y > 65535u || grid.z > 65535u) return B2_ERR_ARG;
-  if (pl->cx)
-    pack_x_kernel<true><<<grid, 256, 0, st>>>((const float*)x, pl->BT[d], K, (uint32_t)pl->nz, pl->n, (uint32_t)pl->kpad[d]);
-  else
-    pack_x_kernel<false><<<grid, 256, 0, st>>>((const float*)x, pl->BT[d], K, (uint32_t)pl->nz, pl->n, (uint32_t)pl->kpad[d]);
+  dim3 grid(pl->nstrips, (unsigned)pl->nsl);
+  const float* xf = (const float*)x;
+  const uint32_t nz = (uint32_t)pl->nz, kpad = (uint32_t)pl->kpad[d];
+  if (pl->mode == MODE_B3) {
+    if (pl->cx) pack_x_kernel<true, MODE_B3><<<grid, 256, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
+    else pack_x_kernel<false, MODE_B3><<<grid, 256, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
+  } else {
+    if (pl->cx) pack_x_kernel<true, MODE_H2><<<grid, 256, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
+    else pack_x_kernel<false, MODE_H2><<<grid, 256, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
+  }
   B2_LAUNCH_CHECK();
   PeerOut po;
   po.n = npeers;
   for (int i = 0; i < 8; ++i) po.p[i] = i < npeers ? (float*)peers_host[i] : nullptr;
-  return pl->bk == 64 ? launch_product<64>(pl, d, (float*)y, po, st) : launch_product<32>(pl, d, (float*)y, po, st);
+  if (pl->mode == MODE_B3)
+    return pl->bk == 64 ? launch_product<MODE_B3, 64>(pl, d, (float*)y, po, st) : launch_product<MODE_B3, 32>(pl, d, (float*)y, po, st);
+  return pl->bk == 64 ? launch_product<MODE_H2, 64>(pl, d, (float*)y, po, st) : launch_product<MODE_H2, 32>(pl, d, (float*)y, po, st);
 }

@@ -394,7 +394,10 @@ extern "C" int b2_dot_multi(b2_ctx* ctx, int k, const void* const* xs, const voi
   if (!ctx || !out_dev || !xs || !ys || k < 1 || k > 4) return B2_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) {
-    zero_out_kernel<<<1, 32, 0, st>>>(out_dev, 2 * k, 0.0);
+    // a rank owning no elements: zero exactly the slots this dtype's layout uses (k doubles for real
+    // dtypes, k (re, im) pairs for complex) -- the caller packs other scalars right behind them
+    const bool cx0 = (dtype == B2_C64 || dtype == B2_C128);
+    zero_out_kernel<<<1, 32, 0, st>>>(out_dev, cx0 ? 2 * k : k, 0.0);
     B2_LAUNCH_CHECK();
     return B2_OK;
   }

@@ -39,6 +39,38 @@ struct StencilParams {
   int nbatch;
 };
 
+// ---- halo rows over NVLink PEER MEMORY inside the stencil kernel (round 2) -----------------------------------
+// Every rank owns a mailbox ("box") in IPC-mapped memory: flags + 2 parities x 2 sides of halo rows.  The first
+// column-tile CTAs of the kernel push this rank's boundary rows straight into the neighbours' boxes (16-byte P2P
+// stores) and publish a system-scope flag; only the CTAs that own the first / last row chunk wait for the
+// neighbour's flag, and they are scheduled LAST, so the exchange hides behind the interior rows: ONE launch per
+// apply, no NCCL call, no side stream (the reference does 2-4 add_ghost_cells exchanges per apply,
+// FirstDerivative.py:221-247, 276-319).  Sequence number and tickets live in device memory (graph-capturable).
+constexpr size_t HALO_HDR = 256;
+struct HaloBox {
+  unsigned long long flag[2][2];   // [parity][side]: side 0 = rows from rank-1, side 1 = rows from rank+1
+};
+struct HaloPeer {
+  char* mine;        // this rank's box (local mapping)
+  char* prev;        // rank-1's box (peer mapping) or nullptr
+  char* next;        // rank+1's box or nullptr
+  size_t cap;        // bytes per (parity, side) slot
+  unsigned long long* seq;   // device: number of completed exchanges
+  unsigned int* tickets;     // device: [0] push ticket, [1] edge ticket, [2] push-done marker
+  int send_lo, send_hi;      // rows this rank sends to rank-1 / rank+1
+};
+__device__ __forceinline__ char* halo_slot(char* box, size_t cap, int par, int side) {
+  return box + HALO_HDR + ((size_t)par * 2 + side) * cap;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // forward taps of global row i (offsets -2..2), before the 1/sampling scale
 // second-derivative taps (MPISecondDerivative, basicoperators/SecondDerivative.py:125-257)
 void fwd_taps2(long long i, long long N, int kind, int edge, double t[NT]) {
@@ -105,6 +137,18 @@ __device__ __forceinline__ const T* row_ptr(const StencilParams& p, const T* x, 
   return (h < p.n_hi) ? hi + h * p.ncols : nullptr;
 }
 
+// row r of the extended block as a 16-byte vector; halo rows (written by a PEER GPU during this kernel in the
+// peer-memory mode) go through the coherent load path, local rows through the read-only one
+template <typename T>
+__device__ __forceinline__ bool load_row(const StencilParams& p, const T* x, const T* lo, const T* hi, long long r,
+                                         size_t coff, Vec16<T>& out) {
+  if (r >= 0 && r < p.nloc) { out = load_vec(x + r * p.ncols + coff); return true; }
+  const T* rp = row_ptr(p, x, lo, hi, r);
+  if (!rp) return false;
+  out = load_vec_coherent(rp + coff);
+  return true;
+}
+
 __device__ __forceinline__ const double* special_taps(const StencilParams& p, long long gi) {
   if (gi < SPECIAL) return p.top[gi];
   if (gi >= p.nglob - SPECIAL) return p.bot[p.nglob - 1 - gi];
@@ -118,28 +162,88 @@ __device__ __forceinline__ const double* special_taps(const StencilParams& p, lo
 // tuning knobs (template parameters): ST_COLS threads along columns, ST_ROWS rows per chunk
 // (per thread), ST_U rows loaded per step.  Variant 0 is the default; B2_STENCIL_VARIANT selects
 // another one at run time (used by profiles/tune_stencil.py).
-template <typename T, int MASK, int ST_ROWS, int ST_U, int ST_COLS>
+template <typename T, int MASK, int ST_ROWS, int ST_U, int ST_COLS, bool PEER = false>
 __global__ void __launch_bounds__(ST_COLS)
 stencil_vec_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restrict__ lo,
-                   const T* __restrict__ hi, const __grid_constant__ StencilParams p) {
+                   const T* __restrict__ hi, const __grid_constant__ StencilParams p,
+                   const HaloPeer hp = HaloPeer{}) {
   constexpr int V = Vec16<T>::N;
   const long long ncv = p.ncols / V;
   // 1-D grid, column tile fastest: concurrently running CTAs cover whole rows
   const long long n_ct = (ncv + ST_COLS - 1) / ST_COLS;
-  const long long ct = (long long)blockIdx.x % n_ct, rc = (long long)blockIdx.x / n_ct;
+  const long long ct = (long long)blockIdx.x % n_ct;
+  long long rc = (long long)blockIdx.x / n_ct;
   x += (size_t)blockIdx.y * (size_t)p.batch_stride;     // batched local problems (blockIdx.y = 0 otherwise)
   y += (size_t)blockIdx.y * (size_t)p.batch_stride;
   const long long cv = ct * ST_COLS + threadIdx.x;
+  [[maybe_unused]] bool edge_cta = false;
+  [[maybe_unused]] unsigned long long seq = 0;
+  [[maybe_unused]] long long n_edge = 0;
+  if constexpr (PEER) {
+    // chunk order: interior chunks first, the chunks next to the neighbours (0, n_rc-2, n_rc-1) LAST
+    const long long n_rc = (p.nloc + ST_ROWS - 1) / ST_ROWS, j = rc;
+    n_edge = n_rc < 3 ? n_rc : 3;
+    if (j < n_rc - n_edge) rc = j + 1;
+    else {
+      const long long e = j - (n_rc - n_edge);
+      rc = (e == 0) ? 0 : n_rc - n_edge + e;
+      edge_cta = true;
+    }
+    seq = *reinterpret_cast<volatile unsigned long long*>(hp.seq) + 1ull;
+    const int par = (int)(seq & 1ull);
+    if (j == 0) {
+      // push my boundary rows into the neighbours' boxes (this CTA's column tile)
+      if (cv < ncv) {
+        const size_t cb = (size_t)cv * 16;
+        if (hp.prev)
+          for (int rr = 0; rr < hp.send_lo; ++rr)
+            stg_stream16(halo_slot(hp.prev, hp.cap, par, 1) + (size_t)rr * p.ncols * sizeof(T) + cb,
+                         ldg_stream16(x + (size_t)rr * p.ncols + (size_t)cv * V));
+        if (hp.next)
+          for (int rr = 0; rr < hp.send_hi; ++rr)
+            stg_stream16(halo_slot(hp.next, hp.cap, par, 0) + (size_t)rr * p.ncols * sizeof(T) + cb,
+                         ldg_stream16(x + (size_t)(p.nloc - hp.send_hi + rr) * p.ncols + (size_t)cv * V));
+      }
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&hp.tickets[0], 1u);
+        if (t == (unsigned int)n_ct - 1u) {      // every column tile of this rank is on its way: publish
+          __threadfence_system();
+          if (hp.prev) st_release_sys_u64(&reinterpret_cast<HaloBox*>(hp.prev)->flag[par][1], seq);
+          if (hp.next) st_release_sys_u64(&reinterpret_cast<HaloBox*>(hp.next)->flag[par][0], seq);
+          *reinterpret_cast<volatile unsigned int*>(&hp.tickets[2]) = 1u;
+        }
+      }
+    }
+    lo = reinterpret_cast<const T*>(halo_slot(hp.mine, hp.cap, par, 0));
+    hi = reinterpret_cast<const T*>(halo_slot(hp.mine, hp.cap, par, 1));
+  }
   const long long r0 = rc * ST_ROWS;
   const long long r1 = (r0 + ST_ROWS < p.nloc) ? r0 + ST_ROWS : p.nloc;
-  if (cv >= ncv) return;
+  if constexpr (PEER) {
+    const int par = (int)(seq & 1ull);
+    const bool needs_lo = hp.prev && p.n_lo > 0 && r0 - R < 0;
+    const bool needs_hi = hp.next && p.n_hi > 0 && r1 - 1 + R >= p.nloc;
+    if (needs_lo || needs_hi) {
+      if (threadIdx.x == 0) {
+        const HaloBox* me = reinterpret_cast<const HaloBox*>(hp.mine);
+        if (needs_lo) while (ld_acquire_sys_u64(&me->flag[par][0]) < seq) { }
+        if (needs_hi) while (ld_acquire_sys_u64(&me->flag[par][1]) < seq) { }
+      }
+      __syncthreads();
+    }
+  }
+  if (PEER ? false : (cv >= ncv)) return;
   const long long g0 = p.row0 + r0, g1 = p.row0 + r1;  // global rows [g0, g1)
   const bool has_special = (g0 < SPECIAL) || (g1 > p.nglob - SPECIAL);
   const size_t coff = (size_t)cv * V;
   const T scale = (T)p.scale;
   const bool do_scale = (p.scale != 1.0);
 
-  if (!has_special) {
+  if (PEER && cv >= ncv) {
+    // inactive column lanes of a peer-mode CTA still take part in the barriers below
+  } else if (!has_special) {
     T c[NT];
 #pragma unroll
     for (int k = 0; k < NT; ++k) c[k] = (T)p.interior[k];
@@ -147,9 +251,7 @@ stencil_vec_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restri
     Vec16<T> w[NT + ST_U - 1];
 #pragma unroll
     for (int j = 0; j < 2 * R; ++j) {
-      const T* rp = row_ptr(p, x, lo, hi, r0 - R + j);
-      if (rp) w[j] = load_vec(rp + coff);
-      else {
+      if (!load_row(p, x, lo, hi, r0 - R + j, coff, w[j])) {
 #pragma unroll
         for (int e = 0; e < V; ++e) w[j].v[e] = (T)0;
       }
@@ -157,9 +259,7 @@ stencil_vec_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restri
     for (long long r = r0; r < r1; r += ST_U) {
 #pragma unroll
       for (int u = 0; u < ST_U; ++u) {
-        const T* rp = (r + u < r1 + R) ? row_ptr(p, x, lo, hi, r + u + R) : nullptr;
-        if (rp) w[2 * R + u] = load_vec(rp + coff);
-        else {
+        if (!(r + u < r1 + R && load_row(p, x, lo, hi, r + u + R, coff, w[2 * R + u]))) {
 #pragma unroll
           for (int e = 0; e < V; ++e) w[2 * R + u].v[e] = (T)0;
         }
@@ -194,9 +294,8 @@ stencil_vec_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restri
       for (int k = 0; k < NT; ++k) {
         const double tk = sp ? sp[k] : p.interior[k];
         if (tk != 0.0) {
-          const T* rp = row_ptr(p, x, lo, hi, r + k - R);
-          if (rp) {
-            Vec16<T> v = load_vec(rp + coff);
+          Vec16<T> v;
+          if (load_row(p, x, lo, hi, r + k - R, coff, v)) {
 #pragma unroll
             for (int e = 0; e < V; ++e) o.v[e] = fma((T)tk, v.v[e], o.v[e]);
           }
@@ -207,6 +306,28 @@ stencil_vec_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restri
         for (int e = 0; e < V; ++e) o.v[e] *= scale;
       }
       store_vec(y + (size_t)r * p.ncols + coff, o);
+    }
+  }
+  if constexpr (PEER) {
+    if (edge_cta) {
+      // the last of the edge CTAs closes the exchange: it has seen BOTH neighbours' flags (so no rank can run
+      // more than one exchange ahead of a neighbour: the two parities never collide) and this rank's push
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&hp.tickets[1], 1u);
+        if (t == (unsigned int)(n_edge * n_ct) - 1u) {
+          const int par = (int)(seq & 1ull);
+          const HaloBox* me = reinterpret_cast<const HaloBox*>(hp.mine);
+          if (hp.prev) while (ld_acquire_sys_u64(&me->flag[par][0]) < seq) { }
+          if (hp.next) while (ld_acquire_sys_u64(&me->flag[par][1]) < seq) { }
+          while (*reinterpret_cast<volatile unsigned int*>(&hp.tickets[2]) == 0u) { }
+          hp.tickets[0] = 0u;
+          hp.tickets[1] = 0u;
+          hp.tickets[2] = 0u;
+          __threadfence();
+          *reinterpret_cast<volatile unsigned long long*>(hp.seq) = seq;
+        }
+      }
     }
   }
 }
@@ -273,6 +394,31 @@ int launch_vec(const void* x, void* y, const void* lo, const void* hi, const Ste
     default:
       stencil_vec_kernel<T, 0x1f, ROWS, U, COLS><<<grid, COLS, 0, st>>>((const T*)x, (T*)y, (const T*)lo,
                                                                         (const T*)hi, p);
+  }
+#undef B2_ST_CASE
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+// peer-memory halo mode: the tuned (4, 4, 128) variant with the exchange fused in
+template <typename T>
+int launch_vec_peer(const void* x, void* y, const StencilParams& p, const HaloPeer& hp, int mask, cudaStream_t st) {
+  constexpr int V = Vec16<T>::N;
+  constexpr int ROWS = 4, U = 4, COLS = 128;
+  const long long nblk = ((p.ncols / V + COLS - 1) / COLS) * ((p.nloc + ROWS - 1) / ROWS);
+  if (nblk > 0x7fffffffLL) return B2_ERR_ARG;
+  const dim3 grid((unsigned)nblk, 1u);
+#define B2_ST_CASE(M)                                                                                       \
+  case M:                                                                                                   \
+    stencil_vec_kernel<T, M, ROWS, U, COLS, true><<<grid, COLS, 0, st>>>((const T*)x, (T*)y, nullptr, nullptr, p, hp); \
+    break;
+  switch (mask) {
+    B2_ST_CASE(0x0c)
+    B2_ST_CASE(0x06)
+    B2_ST_CASE(0x0a)
+    B2_ST_CASE(0x1b)
+    default:
+      stencil_vec_kernel<T, 0x1f, ROWS, U, COLS, true><<<grid, COLS, 0, st>>>((const T*)x, (T*)y, nullptr, nullptr, p, hp);
   }
 #undef B2_ST_CASE
   B2_LAUNCH_CHECK();
@@ -390,6 +536,91 @@ extern "C" int b2_first_derivative(b2_ctx* ctx, const void* x, void* y, const vo
   }
 }
 
+
+extern "C" int b2_second_derivative_halo(int kind, int edge, int adjoint, int* need_lo, int* need_hi);
+
+// ---- peer-memory halo handle ------------------------------------------------------------------------------------
+struct b2_halo {
+  int rank, size;
+  char* box[3];               // [0] rank-1's box (peer mapping or NULL), [1] mine, [2] rank+1's
+  size_t cap;
+  unsigned long long* seq;    // device
+  unsigned int* tickets;      // device, 4 uints
+};
+
+extern "C" size_t b2_halo_bytes(size_t cap_bytes) { return HALO_HDR + 4 * cap_bytes; }
+
+// boxes_host[r]: rank r's box as mapped in THIS process (own pointer for r == rank; only rank +/- 1 are used).
+// Zeroes this rank's flags: callers barrier on the host between creation and the first apply.
+extern "C" int b2_halo_create(int rank, int size, void* const* boxes_host, size_t cap_bytes, b2_halo** out) {
+  if (!out || !boxes_host || size < 1 || rank < 0 || rank >= size || cap_bytes == 0 || (cap_bytes % 16)) return B2_ERR_ARG;
+  b2_halo* h = new b2_halo();
+  h->rank = rank;
+  h->size = size;
+  h->cap = cap_bytes;
+  h->box[0] = rank > 0 ? (char*)boxes_host[rank - 1] : nullptr;
+  h->box[1] = (char*)boxes_host[rank];
+  h->box[2] = rank < size - 1 ? (char*)boxes_host[rank + 1] : nullptr;
+  h->seq = nullptr;
+  h->tickets = nullptr;
+  cudaError_t e = cudaMalloc((void**)&h->seq, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->tickets, 4 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->seq, 0, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->tickets, 0, 4 * sizeof(unsigned int));
+  if (e == cudaSuccess) e = cudaMemset(h->box[1], 0, HALO_HDR);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    if (h->seq) cudaFree(h->seq);
+    if (h->tickets) cudaFree(h->tickets);
+    delete h;
+    return (int)e;
+  }
+  *out = h;
+  return B2_OK;
+}
+
+extern "C" int b2_halo_destroy(b2_halo* h) {
+  if (!h) return B2_OK;
+  if (h->seq) cudaFree(h->seq);
+  if (h->tickets) cudaFree(h->tickets);
+  delete h;
+  return B2_OK;
+}
+
+// One-launch distributed stencil: deriv = 1 (MPIFirstDerivative) or 2 (MPISecondDerivative); the halo rows
+// travel through the peer boxes inside the kernel.  Collective over the ranks of the handle (same call
+// sequence on every rank, one stream); every rank must own at least max(need_lo, need_hi) rows.
+extern "C" int b2_derivative_peer(b2_ctx* ctx, b2_halo* h, const void* x, void* y, size_t nrows_local, size_t ncols,
+                                  size_t row0, size_t nrows_global, int deriv, int kind, int order, int edge,
+                                  double sampling, int adjoint, int dtype, void* stream) {
+  if (!ctx || !h || !x || !y || (deriv != 1 && deriv != 2)) return B2_ERR_ARG;
+  if (dtype != B2_F32 && dtype != B2_F64) return B2_ERR_DTYPE;
+  int need_lo, need_hi;
+  int rc = deriv == 1 ? b2_first_derivative_halo(kind, order, adjoint, &need_lo, &need_hi)
+                      : b2_second_derivative_halo(kind, edge, adjoint, &need_lo, &need_hi);
+  if (rc) return rc;
+  const size_t esz = b2_dtype_size(dtype), V = 16 / esz;
+  if ((long long)nrows_local < (need_lo > need_hi ? need_lo : need_hi)) return B2_ERR_HALO;
+  if (ncols % V || ncols / V < 8 || !b2_aligned16(x) || !b2_aligned16(y)) return B2_ERR_ALIGN;
+  if ((size_t)(need_lo > need_hi ? need_lo : need_hi) * ncols * esz > h->cap) return B2_ERR_WORKSPACE;
+  const int n_lo = h->box[0] ? need_lo : 0, n_hi = h->box[2] ? need_hi : 0;
+  StencilParams p;
+  rc = b2_fd_build_params(&p, n_lo, n_hi, nrows_local, ncols, row0, nrows_global, kind, deriv == 1 ? order : 3, edge,
+                          sampling, adjoint, deriv);
+  if (rc) return rc;
+  HaloPeer hp;
+  hp.mine = h->box[1];
+  hp.prev = h->box[0];
+  hp.next = h->box[2];
+  hp.cap = h->cap;
+  hp.seq = h->seq;
+  hp.tickets = h->tickets;
+  hp.send_lo = h->box[0] ? need_hi : 0;    // rank-1 needs my first need_hi rows as ITS hi halo
+  hp.send_hi = h->box[2] ? need_lo : 0;    // rank+1 needs my last need_lo rows as ITS lo halo
+  const int mask = interior_mask(p.interior);
+  cudaStream_t st = (cudaStream_t)stream;
+  return dtype == B2_F32 ? launch_vec_peer<float>(x, y, p, hp, mask, st) : launch_vec_peer<double>(x, y, p, hp, mask, st);
+}
 
 // ---- MPISecondDerivative per-rank apply (basicoperators/SecondDerivative.py:125-257) -----------------
 extern "C" int b2_second_derivative_halo(int kind, int edge, int adjoint, int* need_lo, int* need_hi) {

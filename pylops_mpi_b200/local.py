@@ -13,7 +13,45 @@ import torch
 
 from . import _lib
 
-__all__ = ["MatrixMult", "LocalOperator"]
+__all__ = ["MatrixMult", "LocalOperator", "apply_into"]
+
+_REAL_OF = {torch.complex64: torch.float32, torch.complex128: torch.float64}
+_CPLX_OF = {torch.float32: torch.complex64, torch.float64: torch.complex128, torch.bfloat16: torch.complex64}
+_OUT_OK = {}
+
+
+def _accepts_out(fn) -> bool:
+    """does this bound method take an ``out=`` keyword?  (signature inspection, cached per function: catching
+    TypeError around the call would mask genuine TypeErrors raised inside the operator and re-run it)"""
+    import inspect
+    key = getattr(fn, "__func__", fn)
+    ok = _OUT_OK.get(key)
+    if ok is None:
+        try:
+            params = inspect.signature(fn).parameters
+            ok = "out" in params or any(p.kind is inspect.Parameter.VAR_KEYWORD for p in params.values())
+        except (TypeError, ValueError):
+            ok = False
+        _OUT_OK[key] = ok
+    return ok
+
+
+def apply_into(oper, x: torch.Tensor, out: torch.Tensor, adjoint: bool) -> None:
+    """``out[...] = oper(x)`` / ``oper^H(x)`` for a rank-local operator, writing in place when the operator
+    supports ``out=`` (the b200 local operators), else through a temporary (cast to ``out``'s dtype)."""
+    fn = oper.rmatvec if adjoint else oper.matvec
+    if _accepts_out(fn):
+        fn(x, out=out)
+    else:
+        _store(out, fn(x))
+
+
+def _store(out: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """out <- y with NumPy-style same-kind casting (complex into real is refused, not silently truncated)"""
+    if y.dtype.is_complex and not out.dtype.is_complex:
+        raise TypeError(f"cannot store a {y.dtype} result into a {out.dtype} output")
+    out.copy_(y.reshape(out.shape))
+    return out
 
 
 class LocalOperator:
@@ -58,17 +96,30 @@ class MatrixMult(LocalOperator):
     def _apply(self, x: torch.Tensor, op: int, out=None) -> torch.Tensor:
         m, n = self.shape
         x = x.reshape(-1)
+        nin, nout = (n, m) if op == _lib.OP_N else (m, n)
+        if x.numel() != nin:
+            raise ValueError(f"dimension mismatch: operator {self.shape}, vector {x.numel()}")
+        if x.dtype.is_complex and not self._xdtype.is_complex:
+            # real operator, complex data: result_type(op, x) is complex (the reference's NumPy promotion) --
+            # apply to the real and imaginary parts instead of dropping the imaginary one
+            rdt = torch.promote_types(self._xdtype, _REAL_OF[x.dtype])
+            yr = self._apply(x.real.contiguous(), op).to(rdt)
+            yi = self._apply(x.imag.contiguous(), op).to(rdt)
+            y = torch.complex(yr, yi)
+            return y if out is None else _store(out, y)
         if x.dtype != self._xdtype:
             x = x.to(self._xdtype)
         if not x.is_contiguous():
             x = x.contiguous()
-        nin, nout = (n, m) if op == _lib.OP_N else (m, n)
-        if x.numel() != nin:
-            raise ValueError(f"dimension mismatch: operator {self.shape}, vector {x.numel()}")
-        y = torch.empty(nout, dtype=self._xdtype, device=x.device) if out is None else out
+        direct = out is not None and out.dtype == self._xdtype and out.is_contiguous() and out.numel() == nout
+        if out is not None and out.numel() != nout:
+            raise ValueError(f"dimension mismatch: operator {self.shape}, out {out.numel()}")
+        y = out if direct else torch.empty(nout, dtype=self._xdtype, device=x.device)
         _lib.check(_lib.lib.b2_gemv(_lib.ctx(), self.A.data_ptr(), n, m, n, x.data_ptr(), y.data_ptr(),
                                     op, _lib.code(self._tdtype), _lib.code(self._xdtype), _lib.stream()),
                    "b2_gemv")
+        if out is not None and not direct:       # caller's buffer has another dtype (e.g. mixed-dtype BlockDiag)
+            return _store(out, y)
         return y
 
     def _matvec(self, x, out=None):
@@ -109,16 +160,20 @@ class _AxisDerivative(LocalOperator):
 
     def _apply(self, x: torch.Tensor, adjoint: int, out=None) -> torch.Tensor:
         x = x.reshape(-1)
-        if x.dtype != self._tdtype:
-            x = x.to(self._tdtype)
+        tdt = self._tdtype
+        if x.dtype.is_complex and not tdt.is_complex:
+            tdt = _CPLX_OF[torch.promote_types(tdt, _REAL_OF[x.dtype])]     # real taps on complex data
+        if x.dtype != tdt:
+            x = x.to(tdt)
         if not x.is_contiguous():
             x = x.contiguous()
-        y = torch.empty_like(x) if out is None else out
+        direct = out is not None and out.dtype == tdt and out.is_contiguous() and out.numel() == x.numel()
+        y = out if direct else torch.empty_like(x)
         n_outer = int(np.prod(self.dims[:self.axis])) if self.axis else 1
         n_axis = self.dims[self.axis]
         n_inner = int(np.prod(self.dims[self.axis + 1:])) if self.axis + 1 < len(self.dims) else 1
-        cx = self._tdtype.is_complex
-        real = {torch.complex64: torch.float32, torch.complex128: torch.float64}.get(self._tdtype, self._tdtype)
+        cx = tdt.is_complex
+        real = _REAL_OF.get(tdt, tdt)
         if cx and n_inner == 1:
             # complex along the innermost axis: the (re, im) pairs are the "inner" dimension
             n_inner = 2
@@ -127,6 +182,8 @@ class _AxisDerivative(LocalOperator):
         _lib.check(_lib.lib.b2_derivative_axis(_lib.ctx(), x.data_ptr(), y.data_ptr(), n_outer, n_axis, n_inner,
                                                self._deriv, self._kind, self.order, int(self.edge), self.sampling,
                                                adjoint, _lib.code(real), _lib.stream()), "b2_derivative_axis")
+        if out is not None and not direct:
+            return _store(out, y)
         return y
 
     def _matvec(self, x, out=None):

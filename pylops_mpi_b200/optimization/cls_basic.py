@@ -44,6 +44,13 @@ class Solver:
         print("-" * nbar + "\n")
 
 
+def _generic(*arrs) -> bool:
+    """True when any operand is not a plain DistributedArray (StackedDistributedArray models / data,
+    test_solver.py:303+): the solvers then run the reference's own sequence of ``dot / + / *`` operations
+    instead of the fused device-scalar step"""
+    return any(not isinstance(a, DistributedArray) for a in arrs)
+
+
 def _absdot(a: DistributedArray, b: DistributedArray) -> float:
     """|a . conj(b)| as the reference computes it (np.abs(a.dot(b.conj())).item())"""
     return float(np.abs(a.dot(b.conj())).item())
@@ -106,7 +113,7 @@ def _lincomb_dev(out: DistributedArray, a_dev: Optional[torch.Tensor], ai: int, 
                  x: DistributedArray, b_dev: Optional[torch.Tensor], bi: int, b_scale: float,
                  y: DistributedArray):
     """out = (a_scale * a_dev[ai]) * x + (b_scale * b_dev[bi]) * y with DEVICE scalars (NULL -> 1)"""
-    o, xv, yv = out._cont(), x._cont(), y._cont()
+    o, xv, yv = out._cont(), out._as_mine(x), out._as_mine(y)   # one dtype for the kernel: the updated array's
     n = o.numel()
     if n:
         _lib.check(_lib.lib.b2_lincomb_dev(_lib.ctx(), o.data_ptr(),
@@ -129,12 +136,30 @@ class CG(Solver):
         self.r = self.y - self.Op.matvec(x)
         self.rank = x.rank
         self.c = self.r.copy()
-        self.kold = _self_dots([self.r])[0]
+        self._gen = _generic(x, self.r)
+        self.kold = _absdot(self.r, self.r) if self._gen else _self_dots([self.r])[0]
         self.cost: List = [float(np.sqrt(self.kold))]
         self.iiter = 0
         return x
 
+    def _step_generic(self, x):
+        """cls_basic.py:127-141 verbatim in operations (stacked arrays)"""
+        Opc = self.Op.matvec(self.c)
+        cOpc = np.abs(self.c.dot(Opc.conj()))
+        a = float((self.kold / cOpc).item())
+        x += a * self.c
+        self.r -= a * Opc
+        k = _absdot(self.r, self.r)
+        b = float(k / self.kold)
+        self.c = self.r + b * self.c
+        self.kold = k
+        self.iiter += 1
+        self.cost.append(float(np.sqrt(self.kold)))
+        return x
+
     def step(self, x, show: bool = False):
+        if self._gen:
+            return self._step_generic(x)
         Opc = self.Op.matvec(self.c)
         cOpc = float(np.abs(self.c.dot(Opc.conj())).item())
         a = float(self.kold / cOpc)
@@ -174,7 +199,7 @@ class CGLS(Solver):
     """cls_basic.py:252-531"""
 
     def _print_step(self, x) -> None:
-        x0 = x.local_array.reshape(-1)[0].item()
+        x0 = (x if isinstance(x, DistributedArray) else x[0]).local_array.reshape(-1)[0].item()
         strx = f"{x0:1.2e}   " if isinstance(x0, complex) else f"{x0:11.4e}        "
         print(f"{self.iiter:6g}       " + strx + f"{self.cost[self.iiter]:11.4e}    {self.cost1[self.iiter]:11.4e}")
         sys.stdout.flush()
@@ -187,6 +212,9 @@ class CGLS(Solver):
         self.niter = niter
         x = x0.copy()
         self.s = self.y - self.Op.matvec(x)
+        self._gen = _generic(x, self.s)
+        if self._gen:
+            return self._setup_generic(x, damp, show)
         r = self.Op.rmatvec(self.s)
         if damp != 0.0:
             r.axpy_(-damp, x)                       # r = Op^H s - damp * x   (:341-342)
@@ -213,9 +241,46 @@ class CGLS(Solver):
             print("    Itn          x[0]              r1norm         r2norm")
         return x
 
+    def _setup_generic(self, x, damp, show):
+        """cls_basic.py:339-366 in the reference's own operations (stacked arrays)"""
+        r = self.Op.rmatvec(self.s) - x * damp
+        self.rank = x.rank
+        self.c = r.copy()
+        self.q = self.Op.matvec(self.c)
+        self.kold = _absdot(r, r)
+        self.cost = [float(self.s.norm().item())]
+        self.cost1 = [np.sqrt(float(self.cost[0] ** 2 + damp * _absdot(x, x)))]
+        self.iiter = 0
+        if show and self.rank == 0:
+            self._print_solver(nbar=65)
+            print(f"damp = {self.damp:10e}\ttol = {self.tol:10e}\tniter = {self.niter}")
+            print("-" * 65 + "\n")
+            print("    Itn          x[0]              r1norm         r2norm")
+        return x
+
+    def _step_generic(self, x, show):
+        """cls_basic.py:389-404 verbatim in operations"""
+        a = float(np.abs(self.kold / (self.q.dot(self.q.conj()) + self.damp * self.c.dot(self.c.conj()))).item())
+        x += a * self.c
+        self.s -= a * self.q
+        r = self.Op.rmatvec(self.s) - self.damp * x
+        k = _absdot(r, r)
+        b = float(k / self.kold)
+        self.c = r + b * self.c
+        self.q = self.Op.matvec(self.c)
+        self.kold = k
+        self.iiter += 1
+        self.cost.append(float(self.s.norm().item()))
+        self.cost1.append(np.sqrt(float(self.cost[self.iiter] ** 2 + self.damp * _absdot(x, x))))
+        if show and self.rank == 0:
+            self._print_step(x)
+        return x
+
     def step(self, x, show: bool = False):
         """One CGLS iteration (cls_basic.py:370-404) with the scalars a, b kept on the device:
         2 Allreduces and ONE host synchronisation per iteration (the reference: 5 and 5)."""
+        if self._gen:
+            return self._step_generic(x, show)
         dev, st = self._dev, self._st
         QQ, CC, K, SS, XX, A_, B_, KOLD = 0, st, 4, 4 + st, 4 + 2 * st, 12, 13, 14
         sub = self.c.sub_comm

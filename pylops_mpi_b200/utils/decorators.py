@@ -5,13 +5,36 @@ grouped NCCL exchange otherwise -- call the body on a ``dims``-shaped array,
 ravel the result."""
 from __future__ import annotations
 
+import os
 from functools import wraps
 from typing import Callable, Optional
 
 import numpy as np
 
 from ..DistributedArray import DistributedArray, Partition
-from .partition import local_split_sizes
+from .partition import local_split_sizes, reshaped_ghost_cells
+
+# Strict-parity mode (SURVEY 8a): the reference's @reshaped only ever talks to rank +/- 1 through add_ghost_cells
+# and raises ValueError when the re-partition deficit exceeds the neighbour's extent (DistributedArray.py:918-923,
+# 935-940) -- e.g. dims (11, 21) at P = 8.  The native general re-partition has no such limit; set
+# B2_STRICT_REFERENCE=1 (or decorators.STRICT_PARITY = True) to get the reference's error instead.
+STRICT_PARITY = os.environ.get("B2_STRICT_REFERENCE", "0") == "1"
+
+
+def _strict_check(x: DistributedArray, dst_sizes) -> None:
+    """raise the reference's add_ghost_cells error when its neighbour-only plan cannot realise this re-partition
+    (raised on EVERY rank -- the reference raises on the sending rank only and leaves the others blocked)"""
+    src = [int(np.prod(s)) for s in x._local_shapes]
+    for r in range(x.size):
+        front, back, _ = reshaped_ghost_cells(dst_sizes, src, r)
+        if r > 0 and front > src[r - 1]:
+            raise ValueError(f"Local Shape at rank={r - 1} along axis=0 should be > {front}: dim(0) "
+                             f"{src[r - 1]} < {front}; to achieve this use NUM_PROCESSES <= "
+                             f"{max(1, int(np.prod(x.global_shape)) // front)}")
+        if r < x.size - 1 and back > src[r + 1]:
+            raise ValueError(f"Local Shape at rank={r + 1} along axis=0 should be > {back}: dim(0) "
+                             f"{src[r + 1]} < {back}; to achieve this use NUM_PROCESSES <= "
+                             f"{max(1, int(np.prod(x.global_shape)) // back)}")
 
 
 def reshaped(func: Optional[Callable] = None, forward: Optional[bool] = None,
@@ -34,6 +57,8 @@ def reshaped(func: Optional[Callable] = None, forward: Optional[bool] = None,
                 ext = local_split_sizes(dims[0], x.size)
                 local_shapes = [(e,) + dims[1:] for e in ext]
             dst = [int(np.prod(s)) for s in local_shapes]
+            if STRICT_PARITY and x.size > 1:
+                _strict_check(x, dst)
             buf = x._repartition_flat(dst).view(local_shapes[x.rank])
             arr = DistributedArray(global_shape=global_shape, base_comm=x.base_comm,
                                    local_shapes=local_shapes, axis=0, dtype=x._tdtype, _buffer=buf,

@@ -245,3 +245,29 @@ def test_local_split_sizes_property(n, P):
     assert len(s) == P and sum(s) == n and max(s) - min(s) <= 1 and s == sorted(s, reverse=True)
     off = offsets(s)
     assert off[0] == 0 and off[-1] == n and len(off) == P + 1
+
+
+@pytest.mark.parametrize("dims", [(11, 21), (600,), (100, 7), (101, 5, 3), (79, 4, 5)])
+@pytest.mark.parametrize("P", [2, 3, 4, 8])
+def test_strict_parity_mode_raises_exactly_where_the_reference_does(dims, P):
+    """B2_STRICT_REFERENCE / decorators.STRICT_PARITY: the native re-partition handles any overlap; the strict
+    check must raise iff the reference's neighbour-only add_ghost_cells plan does (DistributedArray.py:918-923),
+    i.e. iff the oracle's restatement of @reshaped raises for the same split (e.g. (11, 21) at P = 8)."""
+    from types import SimpleNamespace
+    from pylops_mpi_b200.utils import decorators as D
+    from pylops_mpi_b200.utils.partition import local_split_sizes
+    n = int(np.prod(dims))
+    src = local_split_sizes(n, P)
+    ext = local_split_sizes(dims[0], P)
+    dst = [e * int(np.prod(dims[1:])) for e in ext]
+    x = SimpleNamespace(_local_shapes=[(s,) for s in src], size=P, global_shape=(n,))
+    try:
+        o.reshaped_in(o.to_dist(np.arange(float(n)), P), [(e,) + tuple(dims[1:]) for e in ext])
+        ref_raises = False
+    except ValueError:
+        ref_raises = True
+    if ref_raises:
+        with pytest.raises(ValueError, match="Local Shape at rank="):
+            D._strict_check(x, dst)
+    else:
+        D._strict_check(x, dst)

@@ -204,3 +204,40 @@ def test_dottest_config1():
     rmv = lambda a: o.SimArray(o.first_derivative(a.locs, dims, adjoint=True))    # noqa: E731
     ok, xx, yy = o.dottest(mv, rmv, u, v)
     assert ok
+
+
+def test_cgls_blockdiag_cost_is_rounding_noise_below_1e_6():
+    """Conditioning argument behind the tolerance of the multi-rank CGLS parity check (tests/multi_worker.py,
+    tests/parity_checks.py; reference test: tests/test_solver.py:150-196 at P ranks).  The operator is block
+    diagonal with blocks (r+1)^2 ones^T ones + 1e-5 I: P distinct large eigenvalues and a 1e-5 cluster, so CGLS
+    drives the residual to ~1e-8 of its start in P iterations and everything after that is rounding noise.
+    A ONE-ULP relative perturbation of the operator output changes those late cost entries by more than 10 % (and
+    can move the stopping iteration by one) at P = 8, while every entry above 1e-6 * cost[0] is reproduced to
+    1e-9: the achievable parity is 1e-6 of the problem scale, which is what the multi-rank checks assert."""
+    P, ny, nx = 8, 31, 11
+    blocks = []
+    for r in range(P):
+        A = np.ones((ny, nx)) * (r + 1)
+        blocks.append([A.T @ A + 1e-5 * np.eye(nx)])
+    xt = np.random.default_rng(42).normal(1, 10, P * nx)
+
+    def run(eps):
+        rng = np.random.default_rng(0)
+
+        def wrap(locs):
+            return o.SimArray([b * (1 + eps * rng.standard_normal(b.shape)) for b in locs] if eps else locs)
+        mv = lambda v: wrap(o.blockdiag(blocks, v.locs))                    # noqa: E731
+        rmv = lambda v: wrap(o.blockdiag(blocks, v.locs, adjoint=True))     # noqa: E731
+        y = o.SimArray(o.blockdiag(blocks, o.to_dist(xt, P)))
+        return o.cgls(mv, rmv, y, o.SimArray(o.to_dist(np.zeros(P * nx), P)), niter=nx, tol=1e-5)
+
+    x0, _, it0, _, _, c0 = run(0.0)
+    x1, _, it1, _, _, c1 = run(1e-16)
+    k = min(len(c0), len(c1))
+    c0, c1 = np.asarray(c0[:k]), np.asarray(c1[:k])
+    big = c0 > 1e-6 * c0[0]
+    assert abs(it0 - it1) <= 1
+    np.testing.assert_allclose(c1[big], c0[big], rtol=1e-9)                      # well-conditioned part: reproducible
+    assert np.max(np.abs(c1[~big] - c0[~big]) / c0[~big]) > 0.1                  # noise part: > 10 % from ONE ulp
+    np.testing.assert_allclose(c1, c0, rtol=1e-6, atol=1e-6 * c0[0])             # the bound the parity checks use
+    np.testing.assert_allclose(x1.asarray(), x0.asarray(), rtol=1e-6, atol=1e-6 * np.abs(xt).max())
