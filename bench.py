@@ -4,19 +4,22 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--no-extras]
 
 Headline (BASELINE.json metric "... GB/s (FirstDerivative)"): one *step* is one
-``MPIFirstDerivative.matvec`` (centered, order 3, float32) over a row-block
-partitioned array with 32768 x 8192 elements PER GPU (1 GiB in + 1 GiB out per
-GPU, >> the 126 MB L2; weak scaling: global rows = 32768 * N), inputs resident
-in HBM.  ``value`` = algorithmic bytes (2 * 4 B per element, all ranks) / time.
-``e2e`` = the same operator through the host-buffer plugin entry
-(``b2_first_derivative_host``: pinned host arrays in, pinned host arrays out,
-H2D + kernel + D2H inside the timed region).  ``extra`` carries the other
-BASELINE configs (reductions, BlockDiag GEMV / cgls, MatrixMult GF/s,
-Fredholm1) measured in the same run.
+``MPIFirstDerivative.matvec`` (centered, order 3, float32) over the (65536, 8192)
+float32 array of SURVEY 8(d) / BASELINE.md 1b, row-block partitioned over the N
+GPUs (STRONG scaling: 2 GiB in + 2 GiB out in total; per-GPU blocks >= 256 MiB,
+above the 126 MB L2), inputs resident in HBM.  ``value`` = algorithmic bytes
+(2 * 4 B per element) / time.  ``e2e`` = the same operator through the
+host-buffer plugin entry (``b2_first_derivative_host``: pinned host arrays in
+and out, H2D + kernel + D2H inside the timed region).  Before any timing every
+rank runs the parity set of tests/parity_checks.py against the oracle at THIS
+world size (``parity`` in the line; a failure aborts the timing).
+``secondary`` = the MatrixMult half of BASELINE's metric (GF/s on the 32768^2
+bf16 config, with its own roofline and a 256-sampled-rows parity check) and the
+weak-scaling curve of the stencil; ``extra`` = the other BASELINE configs.
 
 ``--impl reference`` times the reference's CPU algorithm for the same operator
-(the NumPy restatement in oracle/, one OS process per host core, each applying
-the per-rank stencil code to its own row block) on a bounded sample.
+on the same global workload (the NumPy restatement in oracle/, one OS process
+per host core, each applying the per-rank stencil code to its own row block).
 """
 from __future__ import annotations
 
@@ -38,9 +41,10 @@ import numpy as np  # noqa: E402
 # rank 0 must print exactly ONE JSON line on stdout: keep NCCL's banner / debug text off it
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
-ROWS_PER_GPU = 32768
+GLOBAL_ROWS = 65536            # SURVEY 8(d) C1-throughput / BASELINE.md 1b: dims (65536, 8192) float32, split over G
 NCOLS = 8192
 METRIC = "MPIFirstDerivative matvec GB/s (algorithmic bytes, centered-3 float32)"
+METRIC2 = "MPIMatrixMult matvec GF/s (bf16 -> fp32, 32768 x 32768, M = 4096)"
 HBM_FALLBACK = 6650.0
 
 
@@ -163,32 +167,33 @@ class CpuRanks:
         return False
 
 
-def cpu_reference_pass(pool, cores: int, rows_per_proc: int, ncols: int, reps: int = 1):
-    """one 'step' of the CPU arm: every process applies the per-rank reference stencil
-    (oracle.first_derivative -> FirstDerivative.py:201-219 incl. its temporaries) to its block"""
-    return pool.step()
+def cpu_split():
+    """the CPU arm runs the WHOLE (65536, 8192) workload: one process per host core, rows split evenly"""
+    cores = min(os.cpu_count() or 1, 64)
+    while GLOBAL_ROWS % cores:
+        cores -= 1
+    return cores, GLOBAL_ROWS // cores
 
 
 def run_reference_arm(args):
-    import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = min(os.cpu_count() or 1, 64)
-    rows_per_proc = 2048           # 64 MiB float32 per process per pass
+    cores, rows_per_proc = cpu_split()
     with CpuRanks(cores, rows_per_proc, NCOLS) as pool:
         for _ in range(max(1, args.warmup // 2)):
-            cpu_reference_pass(pool, cores, rows_per_proc, NCOLS)
+            pool.step()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            cpu_reference_pass(pool, cores, rows_per_proc, NCOLS)
+            pool.step()
         dt = time.perf_counter() - t0
-    nbytes = 2 * 4 * rows_per_proc * NCOLS * cores * args.steps
+    nbytes = 2 * 4 * GLOBAL_ROWS * NCOLS * args.steps
     val = nbytes / dt / 1e9
-    sample = f"{cores} processes x ({rows_per_proc} x {NCOLS}) float32 rows per step (bounded sample of the {ROWS_PER_GPU} x {NCOLS} per-GPU block)"
+    sample = (f"the full ({GLOBAL_ROWS} x {NCOLS}) float32 workload per step: {cores} processes x ({rows_per_proc} x {NCOLS}) rows "
+              "(oracle restatement of FirstDerivative.py:201-219 per rank; the same global workload for every --gpus N)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "GB/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args.gpus),
             "cpu_baseline": {"value": val, "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -198,9 +203,11 @@ def run_reference_arm(args):
 
 def workload_config(n):
     return {"workload": "MPIFirstDerivative matvec, kind=centered order=3 edge=False sampling=1, float32, "
-                        f"dims=({ROWS_PER_GPU}*N, {NCOLS}) row-block partition, N={n}",
-            "rows_per_gpu": ROWS_PER_GPU, "ncols": NCOLS, "global_rows": ROWS_PER_GPU * n,
-            "l2": "per-GPU input 1 GiB >> 126 MB L2 (no flush needed)", "parallelism": f"rows{n}"}
+                        f"dims=({GLOBAL_ROWS}, {NCOLS}) global, row-block partition over N={n} GPUs (strong scaling; "
+                        "SURVEY 8d C1 / BASELINE.md 1b)",
+            "global_rows": GLOBAL_ROWS, "ncols": NCOLS, "rows_per_gpu": GLOBAL_ROWS // n,
+            "l2": f"per-GPU input {GLOBAL_ROWS // n * NCOLS * 4 >> 20} MiB + output of the same size > 126 MB L2 (no flush needed)",
+            "parallelism": f"rows{n}"}
 
 
 # --------------------------------------------------------------------------
@@ -237,16 +244,33 @@ def run_gpu_arm(args):
 
     comm = pm.get_comm_world()
     rank, size = comm.Get_rank(), comm.Get_size()
-    if size != args.gpus:
-        if rank == 0:
-            print(f"warning: --gpus {args.gpus} but world size {size}", file=sys.stderr)
+    if size != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but world size {size}", file=sys.stderr)
     peaks, peak_kind = load_peaks()
     dev = torch.cuda.current_device()
-    N = ROWS_PER_GPU * size
+    if GLOBAL_ROWS % size:
+        raise SystemExit(f"world size {size} does not divide {GLOBAL_ROWS} rows")
+    N = GLOBAL_ROWS
     dims = (N, NCOLS)
-    nloc = ROWS_PER_GPU
+    nloc = N // size
     elem_loc = nloc * NCOLS
     bytes_loc = 2 * 4 * elem_loc
+
+    # ---- parity preamble: the multi-rank paths against the oracle at THIS world size, before any timing ----------
+    parity = None
+    if not args.no_check:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import parity_checks
+        parity = parity_checks.run_all(pm, comm, full_size=True)
+        torch.cuda.synchronize()
+        if parity["failed"]:
+            if rank == 0:      # no timing of a wrong result: report and stop
+                print(json.dumps({"metric": METRIC, "value": 0.0, "unit": "GB/s", "n_gpus": size, "steps": 0,
+                                  "warmup": 0, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+                                  "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                                  "config": workload_config(size), "parity": parity,
+                                  "error": "parity check failed: timing aborted"}))
+            sys.exit(1)
 
     # ---- inputs resident in HBM --------------------------------------------------
     g = torch.Generator(device="cuda").manual_seed(42 + rank)
@@ -266,6 +290,7 @@ def run_gpu_arm(args):
     ms = time_loop(step, args.steps, 0, comm)
     enqueue_ms = time_loop.last_enqueue_ms     # host time to enqueue one step (GPU-bound if << ms_per_step)
     value = bytes_loc * size * args.steps / (ms * 1e-3) / 1e9
+    fused_halo = size > 1 and comm.halo is not None
 
     # ---- roofline of the dominant kernel: live CUDA-event timing of the kernel alone --------
     xl = x.local_array
@@ -288,13 +313,16 @@ def run_gpu_arm(args):
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("stencil_vec_kernel_f32_centered3_bytes_per_launch")
+            tj = json.load(f)
+            per_elem = tj.get("stencil_vec_kernel_f32_centered3_bytes_per_element")
+            traffic = per_elem * elem_loc if per_elem else None
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "stencil_vec_kernel<float, taps{-1,+1}>", "achieved": achieved,
                 "peak": peaks["hbm_gbs"], "peak_kind": f"{peak_kind} copy bandwidth (burst)", "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
-                "algorithmic_bytes_per_launch": bytes_loc, "us_per_launch": kms * 1e3}
+                "algorithmic_bytes_per_launch": bytes_loc, "us_per_launch": kms * 1e3,
+                "note": "algorithmic = 8 B per float32 element (read x once, write y once) x the rows one launch owns"}
 
     # ---- e2e: host buffers through the plugin entry (H2D + kernel + D2H in the timed region) --
     # each rank owns rows [rank*nloc, (rank+1)*nloc) of the replicated host array; only its block
@@ -323,15 +351,27 @@ def run_gpu_arm(args):
     if size > 1:
         e2e_s = comm.allreduce(e2e_s, "max")
     e2e_val = bytes_loc * size * e2e_steps / e2e_s / 1e9
+    # the host-buffer result must equal the device-resident path on the same rows (same kernel, same data)
+    nchk = 64
+    xd = xh[:lo + nchk + 2].cuda()
+    yd = torch.empty(nchk, NCOLS, device="cuda")
+    L.check(L.lib.b2_first_derivative(L.ctx(), xd[lo:].data_ptr(), yd.data_ptr(), xd.data_ptr() if lo else None, lo,
+                                      xd[lo + nchk:].data_ptr(), 2, nchk, NCOLS, rank * nloc, N, L.FD_CENTERED, 3, 0, 1.0,
+                                      0, L.F32, L.stream()), "e2e check")
+    e2e_diff = float((yd.cpu() - yh[:nchk]).abs().max())
     e2e = {"value": e2e_val, "unit": "GB/s", "h2d_bytes_per_step": (nloc + lo + hi) * row_bytes * size,
            "d2h_bytes_per_step": nloc * row_bytes * size, "steps": e2e_steps,
-           "api": "b2_first_derivative_host (pinned host in/out, 3-stream chunk pipeline)"}
-    # spot-check the e2e result against the device path (same data -> same numbers)
-    xchk = torch.as_tensor(xh[lo:lo + 64]).cuda()
-    del xh, yh, xchk
+           "per_gpu_pcie_GB/s_each_way": nloc * row_bytes * e2e_steps / e2e_s / 1e9,
+           "api": "b2_first_derivative_host (pinned host in/out, 3-stream chunk pipeline)",
+           "check_vs_device_path": {"rows": nchk, "max_abs_diff": e2e_diff, "equal": e2e_diff == 0.0}}
+    del xh, yh, xd, yd
 
-    extra = {}
+    secondary, extra = {}, {}
     if not args.no_extras:
+        try:
+            secondary = run_secondary(pm, L, comm, peaks, args)
+        except Exception as exc:
+            secondary = {"error": repr(exc)}
         try:
             extra = run_extras(pm, L, comm, peaks, args)
         except Exception as exc:  # extras must never kill the headline line
@@ -339,30 +379,124 @@ def run_gpu_arm(args):
 
     cpu_baseline = None
     if rank == 0 and size == 1 and not args.no_cpu:
-        import multiprocessing as mp
-        cores = min(os.cpu_count() or 1, 64)
-        rows_per_proc = 2048
+        cores, rows_per_proc = cpu_split()
         with CpuRanks(cores, rows_per_proc, NCOLS) as pool:
-            cpu_reference_pass(pool, cores, rows_per_proc, NCOLS)
+            pool.step()
             reps = 0
             t0 = time.perf_counter()
             while time.perf_counter() - t0 < 10.0 and reps < 50:
-                cpu_reference_pass(pool, cores, rows_per_proc, NCOLS)
+                pool.step()
                 reps += 1
             dt = time.perf_counter() - t0
-        cpu_baseline = {"value": 2 * 4 * rows_per_proc * NCOLS * cores * reps / dt / 1e9, "unit": "GB/s",
+        cpu_baseline = {"value": 2 * 4 * GLOBAL_ROWS * NCOLS * reps / dt / 1e9, "unit": "GB/s",
                         "cores": cores, "kind": "port",
-                        "sample": f"{reps} passes of {cores} processes x ({rows_per_proc} x {NCOLS}) float32 "
-                                  "(oracle restatement of FirstDerivative.py:201-219 per rank)"}
+                        "sample": f"{reps} passes over the full ({GLOBAL_ROWS} x {NCOLS}) float32 workload: {cores} processes x "
+                                  f"({rows_per_proc} x {NCOLS}) (oracle restatement of FirstDerivative.py:201-219 per rank)"}
 
     if rank == 0:
+        launches = 1 if (size == 1 or fused_halo) else 3
         line = {"metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": size, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(size), "roofline": roofline, "cpu_baseline": cpu_baseline,
-                "e2e": e2e, "gpu_launches": args.steps * (1 if size == 1 else 3), "clocks": clocks,
-                "host_enqueue_ms_per_step": enqueue_ms, "extra": extra}
+                "e2e": e2e, "gpu_launches": args.steps * launches,
+                "halo": ("peer-memory push + flags inside the stencil kernel (1 launch / apply)" if fused_halo else
+                         ("none (single rank)" if size == 1 else "grouped ncclSend/Recv on a side stream (3 launches / apply)")),
+                "clocks": clocks, "host_enqueue_ms_per_step": enqueue_ms, "parity": parity,
+                "secondary": secondary, "extra": extra}
         print(json.dumps(line))
+
+
+def run_secondary(pm, L, comm, peaks, args):
+    """second half of BASELINE's metric: MPIMatrixMult GF/s on config 4 (32768 x 32768 bf16 -> fp32) through the
+    operator, plus the weak-scaling curve of the headline stencil.  Each figure carries its own roofline."""
+    import torch
+    rank, size = comm.Get_rank(), comm.Get_size()
+    out = {"metric": METRIC2, "unit": "GF/s"}
+    hbm, tpk = peaks["hbm_gbs"], peaks.get("bf16_tflops", 1590.0)
+    grids = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
+    if size in grids:
+        Pr, Pc = grids[size]
+        Ng = Kg = 32768
+        Mg = 4096
+        bn, bkA, bkX, bm = Ng // Pr, Kg // Pc, Kg // Pr, Mg // Pc
+
+        def a_tile(r):
+            return (torch.randn(bn, bkA, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1 + r)) / 181).to(torch.bfloat16)
+
+        def x_tile(r):
+            return torch.randn(bkX, bm, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1001 + r))
+        At = a_tile(rank)
+        modes = {}
+        import parity_checks
+        for name, kw in (("stationary", {"stationary": True}), ("summa", {}), ("replicated", {"replicate": True})):
+            if size == 1 and name != "summa":
+                continue
+            try:
+                Sop = pm.MPIMatrixMult(At, Mg, kind="summa", dtype="bfloat16", grid=(Pr, Pc), **kw)
+            except TypeError:
+                continue
+            xs = pm.DistributedArray(global_shape=Kg * Mg, local_shapes=[bkX * bm] * size, dtype=np.float32)
+            xs.local_array.copy_(x_tile(rank).reshape(-1))
+            y = Sop.matvec(xs)
+            torch.cuda.synchronize()
+            ok, det = parity_checks.sampled_rows_check(pm, comm, Sop, a_tile, x_tile, y, Ng, Kg, Mg, Pr, Pc, nrows=256)
+            oks = comm.allgather(bool(ok)) if size > 1 else [bool(ok)]
+            ms = time_loop(lambda: Sop.matvec(xs), 5, 2, comm)
+            fl = 2.0 * Ng * Kg * Mg
+            tf = fl * 5 / (ms * 1e-3) / 1e12
+            ms2 = time_loop(lambda: Sop.rmatvec(y), 3, 1, comm)
+            modes[name] = {"GF/s": tf * 1e3, "TF/s": tf, "ms": ms / 5, "adjoint_ms": ms2 / 3,
+                           "frac_of_N_x_burst_peak": tf / (size * tpk),
+                           "frac_of_N_x_sustained_peak": tf / (size * peaks.get("bf16_tflops_sustained", tpk)),
+                           "parity_256_sampled_rows_vs_fp64": {"ok": all(oks), "detail": det}}
+            del Sop, xs, y
+        best = "stationary" if "stationary" in modes else "summa"
+        out["value"] = modes[best]["GF/s"]
+        out["layout"] = f"{best}: one copy of A per GPU on a {Pr} x {Pc} grid (the reference's 2-D tile layout)"
+        out["config"] = {"workload": f"MPIMatrixMult 32768 x 32768 bf16 -> fp32, M = 4096 columns, grid {Pr}x{Pc}",
+                         "flop_per_apply": 2.0 * Ng * Kg * Mg}
+        tp = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                tp = json.load(f).get("gemm_bf16_tc2_tensor_pipe_pct")
+        except Exception:
+            pass
+        out["roofline"] = {"bound": "tensor", "kernel": "gemm_bf16_tc2_kernel (tcgen05 cta_group::2, 256x256x64 tiles)",
+                           "achieved": modes[best]["TF/s"] / size, "peak": tpk, "unit": "TFLOP/s per GPU",
+                           "frac": modes[best]["TF/s"] / (size * tpk), "tensor_pipe_pct_ncu": tp,
+                           "peak_kind": "measured cuBLAS bf16 8192^3 burst (MEASURED_PEAKS.json)"}
+        out["modes"] = modes
+        del At
+        # config 4 (i), the literal "32768-vec": single right-hand side, HBM-bound GEMV through the operator
+        try:
+            At1 = (torch.randn(Ng // size, Kg, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1 + rank)) / 181).to(torch.bfloat16)
+            Sop = pm.MPIMatrixMult(At1, 1, kind="summa", dtype="bfloat16", grid=(size, 1), replicate=True)
+            xs = pm.DistributedArray(global_shape=Kg, local_shapes=[Kg // size] * size, dtype=np.float32)
+            xs.local_array.normal_()
+            torch.cuda.synchronize()
+            time.sleep(0.5)
+            ms = time_loop(lambda: Sop.matvec(xs), 20, 10, comm)
+            gb = 2.0 * Ng * Kg * 20 / (ms * 1e-3) / 1e9
+            out["m1_32768_vec"] = {"us": ms / 20 * 1e3, "GB/s_A": gb, "GF/s": gb, "frac_hbm": gb / (size * hbm),
+                                   "layout": f"1-D row panels, grid {size}x1", "bound": "hbm (1 flop/B)"}
+            del Sop, xs, At1
+        except Exception as exc:
+            out["m1_32768_vec"] = {"error": repr(exc)}
+    # weak-scaling curve of the headline stencil (the N = 1 block on every GPU)
+    nloc = GLOBAL_ROWS
+    xw = pm.DistributedArray(global_shape=nloc * size * NCOLS, dtype=np.float32)
+    xw.local_array.normal_()
+    Fw = pm.MPIFirstDerivative((nloc * size, NCOLS), kind="centered", order=3, dtype=np.float32)
+    hold = {}
+
+    def stepw():
+        hold["y"] = Fw.matvec(xw)
+    ms = time_loop(stepw, 10, 3, comm)
+    v = 2 * 4 * nloc * NCOLS * size * 10 / (ms * 1e-3) / 1e9
+    out["fd_weak_scaling"] = {"GB/s": v, "rows_per_gpu": nloc, "ms_per_step": ms / 10, "frac_hbm_per_gpu": v / size / hbm,
+                              "scaling": "weak"}
+    return out
 
 
 def run_extras(pm, L, comm, peaks, args):
@@ -377,7 +511,7 @@ def run_extras(pm, L, comm, peaks, args):
         return nbytes * k / (ms_total * 1e-3) / 1e9
 
     # --- FirstDerivative variants (per-GPU kernel, device resident) -------------------
-    nloc, ncols = ROWS_PER_GPU, NCOLS
+    nloc, ncols = 32768, NCOLS
     for name, dt, code, kind, order, adj in (("fd_centered3_adj_f32", torch.float32, L.F32, L.FD_CENTERED, 3, 1),
                                              ("fd_centered5_f32", torch.float32, L.F32, L.FD_CENTERED, 5, 0),
                                              ("fd_forward_f32", torch.float32, L.F32, L.FD_FORWARD, 3, 0),
@@ -493,64 +627,6 @@ def run_extras(pm, L, comm, peaks, args):
     except Exception as exc:
         out["gemm_bf16_8192^3"] = {"unavailable": repr(exc)}
     del Ab, bop
-    # config 4 through the operator: MPIMatrixMult SUMMA, 32768 x 32768 bf16 -> fp32, grid Pr x Pc
-    try:
-        grids = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}
-        if size in grids:
-            Pr, Pc = grids[size]
-            Ng = Kg = 32768
-            ri, ci = divmod(rank, Pc)
-            At = (torch.randn(Ng // Pr, Kg // Pc, device="cuda",
-                              generator=torch.Generator(device="cuda").manual_seed(1 + rank)) / 181).to(torch.bfloat16)
-            for Mg in (4096, 1):
-                if Mg % Pc:
-                    Mg = Pc
-                for rep in (False, True):
-                    Sop = pm.MPIMatrixMult(At, Mg, kind="summa", dtype="bfloat16", grid=(Pr, Pc), replicate=rep)
-                    sizes = [(Kg // Pr) * (Mg // Pc)] * size
-                    xs = pm.DistributedArray(global_shape=Kg * Mg, local_shapes=sizes, dtype=np.float32)
-                    xs.local_array.normal_()
-                    # sub-millisecond applies (M = 1 / Pc) need more launches to reach a steady state: with 5 timed
-                    # steps the first, cold ones dominated (0.53 ms reported vs 0.35 ms steady, profiles/r01_diag_matmul_m1.json)
-                    kk, ww = (5, 2) if Mg > 64 else (20, 10)
-                    if Mg <= 64:        # let the power cap recover after the tensor-core runs (HBM-bound GEMV follows)
-                        torch.cuda.synchronize()
-                        time.sleep(0.5)
-                    ms = time_loop(lambda: Sop.matvec(xs), kk, ww, comm)
-                    fl = 2.0 * Ng * Kg * Mg
-                    key = f"{'replicated' if rep else 'summa'}_bf16_32768_M{Mg}_grid{Pr}x{Pc}"
-                    out[key] = {"TF/s": fl * kk / (ms * 1e-3) / 1e12, "ms": ms / kk,
-                                "frac_tensor_total": fl * kk / (ms * 1e-3) / 1e12 / (size * peaks.get("bf16_tflops", 1590.0)),
-                                "GB/s_A": 2.0 * Ng * Kg * kk / (ms * 1e-3) / 1e9,
-                                "frac_hbm_A": 2.0 * Ng * Kg * kk / (ms * 1e-3) / 1e9 / (size * hbm)}
-                    k2, w2 = (3, 1) if Mg > 64 else (10, 3)
-                    ms = time_loop(lambda: Sop.rmatvec(Sop.matvec(xs)), k2, w2, comm)
-                    out[key]["fwd+adj_ms"] = ms / k2
-                    del Sop, xs
-            del At
-    except Exception as exc:
-        out["summa_bf16_32768"] = {"error": repr(exc)}
-    if size > 1:
-        # BASELINE config 4 (i), the literal "32768-vec": 1-D row panels (grid P x 1, replicated mode) read every byte of A
-        # exactly once per apply -- the 2-D grids above re-read A Pc times when M < Pc
-        try:
-            Ng = Kg = 32768
-            At = (torch.randn(Ng // size, Kg, device="cuda",
-                              generator=torch.Generator(device="cuda").manual_seed(1 + rank)) / 181).to(torch.bfloat16)
-            Sop = pm.MPIMatrixMult(At, 1, kind="summa", dtype="bfloat16", grid=(size, 1), replicate=True)
-            xs = pm.DistributedArray(global_shape=Kg, local_shapes=[Kg // size] * size, dtype=np.float32)
-            xs.local_array.normal_()
-            torch.cuda.synchronize()
-            time.sleep(0.5)
-            ms = time_loop(lambda: Sop.matvec(xs), 20, 10, comm)
-            gb = 2.0 * Ng * Kg * 20 / (ms * 1e-3) / 1e9
-            out[f"replicated_bf16_32768_M1_grid{size}x1"] = {"ms": ms / 20, "GB/s_A": gb, "frac_hbm_A": gb / (size * hbm),
-                                                             "GF/s": 2.0 * Ng * Kg * 20 / (ms * 1e-3) / 1e9}
-            ms = time_loop(lambda: Sop.rmatvec(Sop.matvec(xs)), 10, 3, comm)
-            out[f"replicated_bf16_32768_M1_grid{size}x1"]["fwd+adj_ms"] = ms / 10
-            del Sop, xs, At
-        except Exception as exc:
-            out[f"replicated_bf16_32768_M1_grid{size}x1"] = {"error": repr(exc)}
     # --- config 5: Fredholm1 (64 slices per GPU, 256 x 256 x 64, complex64) -------------------
     nsl, ns, nr, nv = 64, 256, 256, 64
     G = torch.randn(nsl, ns, nr, device="cuda", dtype=torch.complex64)
@@ -578,6 +654,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the multi-rank parity preamble")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -94,6 +94,12 @@ int b2_dot_multi(b2_ctx* ctx, int k, const void* const* xs, const void* const* y
 int b2_scalar_div(double* out_dev, const double* num_dev, const double* den1_dev,
                   const double* den2_dev, double alpha, void* stream);
 
+/* Device-side history of solver scalars: hist[it * nvals + j] = |src[j * stride]| (skipped when it >= cap), then the
+ * optional scalar copy *copy_dst = *copy_src (kold <- k, cls_basic.py:397) and ++(*it_dev) (uint64).  With it a block of
+ * CGLS iterations (cls_basic.py:370-404) needs no host synchronisation and can be replayed as a CUDA graph. */
+int b2_history_push(const double* src_dev, int nvals, int stride, double* hist_dev, void* it_dev, size_t cap,
+                    double* copy_dst_dev, const double* copy_src_dev, void* stream);
+
 /* ---- ISTA / FISTA model update ("next" row; optimization/cls_sparsity.py:270-343, 578-662) in ONE pass:
  *   u = base + alpha*g (g may be NULL);  v = threshold_kind(u, thresh) (_apply_thresh, cls_sparsity.py:21-46);
  *   xnew = v;  znew = v + c*(v - xold) (znew may be NULL; FISTA's auxiliary model, :640-644);
@@ -167,6 +173,20 @@ int b2_gemv(b2_ctx* ctx, const void* A, size_t lda, size_t m, size_t n, const vo
 int b2_gemm_bf16(b2_ctx* ctx, const void* A, size_t lda, const void* B, size_t ldb, float* C,
                  size_t ldc, size_t m, size_t n, size_t k, int op_a, int accumulate,
                  void* stream);
+/* Stationary-A MPIMatrixMult (round 2): A tiles are operator state and never move; per apply the small operand is
+ * all-gathered (cast to bf16 on the fly) and the partial products are reduce-scattered by the GEMM epilogue itself.
+ *   b2_cast_bf16_multi: float32 tile -> bfloat16, stored to ndst <= 8 destinations (local or IPC-mapped peers):
+ *                       the X / Y panel broadcasts of MatrixMult.py:663-670, 742-763 as ONE read of the tile.
+ *   b2_gemm_bf16_seg  : op(A) B on tcgen05 with the output columns cut into nseg <= 8 segments of seg_cols
+ *                       (multiple of 32) columns, segment c written to segs_host[c] (leading dimension ldc) -- peer
+ *                       GPUs' staging buffers, i.e. the reduce-scatter rides on the epilogue's NVLink stores.
+ *   b2_sum_slots      : out[rows x cols] = sum_s slots[s * slot_stride + r * ld_in + c] in slot order. */
+int b2_cast_bf16_multi(b2_ctx* ctx, const float* src, size_t ld_src, size_t rows, size_t cols,
+                       void* const* dsts_host, int ndst, size_t ld_dst, void* stream);
+int b2_gemm_bf16_seg(b2_ctx* ctx, const void* A, size_t lda, const void* B, size_t ldb, float* const* segs_host,
+                     int nseg, size_t seg_cols, size_t ldc, size_t m, size_t n, size_t k, int op_a, void* stream);
+int b2_sum_slots(b2_ctx* ctx, const float* slots, size_t slot_stride, int nslots, size_t ld_in, float* out,
+                 size_t rows, size_t cols, void* stream);
 /* generic SIMT tile product for the dtypes tensor cores do not serve
  * (f32/f64/c64/c128 parity cases of tests/test_matrixmult.py) */
 int b2_gemm(b2_ctx* ctx, const void* A, size_t lda, const void* B, size_t ldb, void* C, size_t ldc,

@@ -77,6 +77,7 @@ def _load():
         "b2_norm_partial": ([vp, vp, sz, i, i, d, vp, vp], i),
         "b2_dot_multi": ([vp, i, C.POINTER(vp), C.POINTER(vp), sz, i, i, vp, vp], i),
         "b2_scalar_div": ([vp, vp, vp, vp, d, vp], i),
+        "b2_history_push": ([vp, i, i, vp, vp, sz, vp, vp, vp], i),
         "b2_sparse_update": ([vp, vp, vp, d, vp, d, i, vp, vp, d, vp, sz, i, vp], i),
         "b2_first_derivative": ([vp, vp, vp, vp, i, vp, i, sz, sz, sz, sz, i, i, i, d, i, i, vp], i),
         "b2_first_derivative_halo": ([i, i, i, C.POINTER(i), C.POINTER(i)], i),
@@ -91,6 +92,9 @@ def _load():
         "b2_gemv": ([vp, vp, sz, sz, sz, vp, vp, i, i, i, vp], i),
         "b2_gemm_bf16": ([vp, vp, sz, vp, sz, vp, sz, sz, sz, sz, i, i, vp], i),
         "b2_gemm": ([vp, vp, sz, vp, sz, vp, sz, sz, sz, sz, i, i, i, vp], i),
+        "b2_cast_bf16_multi": ([vp, vp, sz, sz, sz, C.POINTER(vp), i, sz, vp], i),
+        "b2_gemm_bf16_seg": ([vp, vp, sz, vp, sz, C.POINTER(vp), i, sz, sz, sz, sz, sz, i, vp], i),
+        "b2_sum_slots": ([vp, vp, sz, i, sz, vp, sz, sz, vp], i),
         "b2_batched_gemm": ([vp, vp, vp, vp, sz, sz, sz, sz, i, i, vp], i),
         "b2_batched_gemm_allgather": ([vp, vp, vp, vp, C.POINTER(vp), i, sz, sz, sz, sz, i, i, vp], i),
         "b2_fredholm_plan_create": ([vp, vp, sz, sz, sz, sz, i, C.POINTER(vp)], i),

@@ -95,6 +95,19 @@ def _xdtype(adt: torch.dtype) -> torch.dtype:
     return torch.float32 if adt is torch.bfloat16 else adt
 
 
+def _cast_bf16(X: torch.Tensor) -> torch.Tensor:
+    """float32 (k x ncol, contiguous) -> bfloat16 through the library's cast kernel (no eager torch pass)"""
+    import ctypes as C
+    if X.dtype is not torch.float32 or not X.is_contiguous():
+        return X.to(torch.bfloat16)
+    out = torch.empty(X.shape, dtype=torch.bfloat16, device=X.device)
+    rows, cols = (X.shape[0], X.shape[1]) if X.dim() == 2 else (1, X.numel())
+    dst = (C.c_void_p * 1)(out.data_ptr())
+    _lib.check(_lib.lib.b2_cast_bf16_multi(_lib.ctx(), X.data_ptr(), cols, rows, cols, dst, 1, cols, _lib.stream()),
+               "b2_cast_bf16_multi")
+    return out
+
+
 def tile_product(A: torch.Tensor, X: torch.Tensor, Y: torch.Tensor, op: int, accumulate: bool):
     """Y (+)= op(A) X on the device.  A: 2-D tile; X: (k, ncol); Y: (m, ncol) contiguous."""
     m_a, n_a = A.shape
@@ -120,7 +133,7 @@ def tile_product(A: torch.Tensor, X: torch.Tensor, Y: torch.Tensor, op: int, acc
                 _lib.check(_lib.lib.b2_gemv(ctx, A.data_ptr(), n_a, m_a, n_a, X.data_ptr(), Y.data_ptr(),
                                             op, _lib.BF16, _lib.F32, st), "b2_gemv")
             return Y
-        Xb = X if X.dtype is torch.bfloat16 else X.to(torch.bfloat16)
+        Xb = X if X.dtype is torch.bfloat16 else _cast_bf16(X)
         _lib.check(_lib.lib.b2_gemm_bf16(ctx, A.data_ptr(), n_a, Xb.data_ptr(), ncol, Y.data_ptr(), ncol,
                                          m, ncol, k, op, int(accumulate), st), "b2_gemm_bf16")
         return Y
@@ -225,8 +238,9 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
     """
 
     def __init__(self, A, M: int, saveAt: bool = False, base_comm=COMM_WORLD, dtype="float64",
-                 base_comm_nccl=None, grid=None, replicate: bool = False) -> None:
+                 base_comm_nccl=None, grid=None, replicate: bool = False, stationary: bool = False) -> None:
         self._replicate = bool(replicate)
+        self._stationary = bool(stationary)
         base_comm = resolve(base_comm)
         rank, size = base_comm.Get_rank(), base_comm.Get_size()
         if grid is None:
@@ -273,6 +287,105 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
         self._side = None
         if self._replicate:
             self._build_replicas()
+        if self._stationary:
+            self._setup_stationary()
+
+    # ---- stationary-A mode: A never moves; X / Y panels are all-gathered, partial products reduce-scattered -------
+    def _setup_stationary(self):
+        """SUMMA re-broadcasts the STATIC A panels on every apply (MatrixMult.py:663-670: 768 MiB received per rank
+        per apply at 32768^2 / 2x4) -- A is operator state, X changes.  Stationary-A keeps ONE copy of A per GPU in
+        the reference's 2-D tile layout and moves only the small operand and the partial results:
+          forward  Y_ij = sum_j' A_ij' X_j'j :  (1) every X tile is cast to bf16 and pushed (P2P stores) into the
+                   gathered-operand arena of the ranks whose A tile covers its K range, (2) ONE local tcgen05 product
+                   A_ij (bn x kA) . Xg (kA x M) whose epilogue stores column block c straight into rank (i, c)'s
+                   staging slot j over NVLink (the reduce-scatter rides on the epilogue), (3) fold the Pc slots.
+          adjoint  the same with A^H: gather Y along the grid row, one product per A panel, staging at rank (r, c).
+        Two flag barriers per apply (peer-memory mailbox kernels); ~4x fewer NVLink bytes than broadcasting A at
+        M = 4096 and no replication of A (cf. ``replicate=True``)."""
+        import ctypes as C
+        comm = self.base_comm
+        A0 = self._A_panels[0]
+        if A0.dtype is not torch.bfloat16:
+            raise NotImplementedError("stationary=True serves the bf16 -> fp32 tensor-core path")
+        if comm.Get_size() > 8:
+            raise NotImplementedError("stationary=True maps at most 8 peers")
+        self._kA = self._w * self._pa
+        if self._bm % 32 or self._kA % 8 or self._bn % 8:
+            raise NotImplementedError("stationary=True needs M/Pc % 32 == 0 and 8-aligned tile extents")
+        if comm.Get_size() > 1 and comm.peer is None:
+            raise NotImplementedError("stationary=True needs CUDA IPC peer access between the ranks")
+        self._A_full = (torch.cat(self._A_panels, dim=1) if self._pa > 1 else self._A_panels[0]).contiguous()
+        Mp = self._bm * self._Pc
+        bkX = self._w * self._px
+        self._st_Mp = Mp
+        sizes = {"XG": self._kA * Mp * 2, "YG": self._bn * Mp * 2,
+                 "SF": self._Pc * self._bn * self._bm * 4, "SA": self._Pr * bkX * self._bm * 4}
+        self._st = {k: comm.symm_alloc(v) for k, v in sizes.items()}      # name -> (my_ptr, ptrs by world rank)
+        self._st_flag = torch.zeros(1, dtype=torch.float64, device="cuda")
+        self._st_keep = []
+        comm.Barrier()
+
+    def _st_barrier(self):
+        """stream-ordered cross-rank barrier: completes when every rank's preceding kernels (and their peer stores)
+        have completed"""
+        allreduce_(self.base_comm, self._st_flag, SUM)
+
+    def _apply_stationary(self, x: DistributedArray, adjoint: bool) -> DistributedArray:
+        import ctypes as C
+        lib, ctx, st = _lib.lib, _lib.ctx(), _lib.stream()
+        Pr, Pc, pa, px, w = self._Pr, self._Pc, self._pa, self._px, self._w
+        bn, bm, Mp, kA = self._bn, self._bm, self._st_Mp, self._kA
+        bkX = w * px
+        i, j = self._row_id, self._col_id
+        rank_of = lambda r, c: r * Pc + c          # noqa: E731
+        rows_in, full_in = (bn, self.N) if adjoint else (bkX, self.K)
+        rows_out, full_out = (bkX, self.K) if adjoint else (bn, self.N)
+        y = DistributedArray(global_shape=(full_out * self.M), mask=x.mask,
+                             local_shapes=self._tile_sizes(rows_out, full_out), partition=Partition.SCATTER,
+                             dtype=torch.float32, base_comm=x.base_comm)
+        x_block, _, local_m = self._padded_block(x, rows_in, full_in, torch.float32)
+        local_out = self._extent(rows_out, full_out, i, Pr)
+
+        def cast_to(src, rows, dst_ptrs):
+            arr = (C.c_void_p * len(dst_ptrs))(*dst_ptrs)
+            _lib.check(lib.b2_cast_bf16_multi(ctx, src.data_ptr(), bm, rows, bm, arr, len(dst_ptrs), Mp, st),
+                       "b2_cast_bf16_multi")
+
+        def gemm_seg(a_ptr, lda, b_ptr, seg_ptrs, m, k, op):
+            arr = (C.c_void_p * len(seg_ptrs))(*seg_ptrs)
+            _lib.check(lib.b2_gemm_bf16_seg(ctx, a_ptr, lda, b_ptr, Mp, arr, len(seg_ptrs), bm, bm, m, Mp, k, op, st),
+                       "b2_gemm_bf16_seg")
+
+        if not adjoint:
+            XG, SF = self._st["XG"], self._st["SF"]
+            for lx in range(px):                 # my X panels -> the ranks whose A tile owns that K range
+                l = i * px + lx
+                jc, la = l // pa, l % pa
+                dsts = [XG[1][rank_of(r, jc)] + ((la * w) * Mp + j * bm) * 2 for r in range(Pr)]
+                cast_to(x_block[lx * w:(lx + 1) * w], w, dsts)
+            self._st_barrier()
+            segs = [SF[1][rank_of(i, c)] + (j * bn * bm) * 4 for c in range(Pc)]
+            gemm_seg(self._A_full.data_ptr(), kA, XG[0], segs, bn, kA, _lib.OP_N)
+            self._st_barrier()
+            slots, nslots, rows_blk = SF[0], Pc, bn
+        else:
+            YG, SA = self._st["YG"], self._st["SA"]
+            dsts = [YG[1][rank_of(i, c)] + (j * bm) * 2 for c in range(Pc)]
+            cast_to(x_block, bn, dsts)
+            self._st_barrier()
+            for la in range(pa):                 # one product per A panel: its rows land in X-tile row block r
+                l = j * pa + la
+                r, lx = l // px, l % px
+                segs = [SA[1][rank_of(r, c)] + (i * bkX * bm + lx * w * bm) * 4 for c in range(Pc)]
+                gemm_seg(self._A_full.data_ptr() + la * w * 2, kA, YG[0], segs, w, bn, _lib.OP_H)
+            self._st_barrier()
+            slots, nslots, rows_blk = SA[0], Pr, bkX
+        direct = (local_out == rows_blk and local_m == bm)
+        out = y.local_array if direct else torch.empty(rows_blk * bm, dtype=torch.float32, device=x_block.device)
+        _lib.check(lib.b2_sum_slots(ctx, slots, rows_blk * bm, nslots, bm, out.data_ptr(), rows_blk, bm, st), "b2_sum_slots")
+        if not direct:
+            y.local_array.copy_(out.view(rows_blk, bm)[:local_out, :local_m].reshape(-1))
+        return y
 
     # ---- replicated-panel mode (B200-first: spend HBM, not NVLink) --------------------------------
     def _build_replicas(self):
@@ -329,7 +442,7 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
                              dtype=xdt, base_comm=x.base_comm)
         x_block, _, local_m = self._padded_block(x, rows_in, full_in, xdt)
         if self._A_row.dtype is torch.bfloat16 and self._bm > 1:
-            x_block = x_block.to(torch.bfloat16)          # halves the allgather payload
+            x_block = _cast_bf16(x_block)                 # halves the allgather payload
         Xcol = self._gather_col(x_block)
         local_out = self._extent(rows_out, full_out, self._row_id, self._Pr)
         direct = (local_out == rows_out and local_m == self._bm)
@@ -435,6 +548,8 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
     def _matvec(self, x: DistributedArray) -> DistributedArray:
         if x.partition != Partition.SCATTER:
             raise ValueError(f"x should have partition={Partition.SCATTER} Got {x.partition} instead...")
+        if self._stationary:
+            return self._apply_stationary(x, False)
         if self._replicate:
             return self._apply_replicated(x, False)
         xdt = _xdtype(self._A_panels[0].dtype)
@@ -473,6 +588,8 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
     def _rmatvec(self, x: DistributedArray) -> DistributedArray:
         if x.partition != Partition.SCATTER:
             raise ValueError(f"x should have partition={Partition.SCATTER}. Got {x.partition} instead.")
+        if self._stationary:
+            return self._apply_stationary(x, True)
         if self._replicate:
             return self._apply_replicated(x, True)
         xdt = _xdtype(self._A_panels[0].dtype)
@@ -511,12 +628,13 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
 
 
 def MPIMatrixMult(A, M: int, saveAt: bool = False, base_comm=COMM_WORLD, kind: str = "summa",
-                  dtype="float64", base_comm_nccl=None, grid=None, replicate: bool = False):
+                  dtype="float64", base_comm_nccl=None, grid=None, replicate: bool = False, stationary: bool = False):
     """Factory with the reference's signature (MatrixMult.py:770-874); ``grid=(Pr, Pc)`` is the
     rectangular-grid extension of the SUMMA variant, ``replicate=True`` its replicated-panel mode
     (A row / column panels kept per rank, one small allgather + one local product per apply)."""
     if kind == "summa":
-        return _MPISummaMatrixMult(A, M, saveAt, base_comm, dtype, base_comm_nccl, grid=grid, replicate=replicate)
+        return _MPISummaMatrixMult(A, M, saveAt, base_comm, dtype, base_comm_nccl, grid=grid, replicate=replicate,
+                                   stationary=stationary)
     elif kind == "block":
         return _MPIBlockMatrixMult(A, M, saveAt, base_comm, dtype, base_comm_nccl)
     else:

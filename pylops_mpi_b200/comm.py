@@ -167,6 +167,29 @@ class Comm:
                 setattr(self, attr + "_failed", True)
         return getattr(self, attr, None)
 
+    def symm_alloc(self, nbytes: int):
+        """COLLECTIVE: every rank allocates ``nbytes`` of IPC-mappable device memory and maps every peer's
+        buffer; returns ``(my_ptr, ptrs)`` with ``ptrs[r]`` = rank r's buffer as addressable from this process
+        (``ptrs[rank] == my_ptr``).  Used for the peer-memory arenas of the fused compute + collective kernels."""
+        from . import _lib
+        ptr = C.c_void_p()
+        _lib.check(_lib.lib.b2_symm_alloc(max(int(nbytes), 16), C.byref(ptr)), "b2_symm_alloc")
+        if self._size == 1:
+            return ptr.value, [ptr.value]
+        h = (C.c_char * 64)()
+        _lib.check(_lib.lib.b2_ipc_get_handle(ptr, h), "b2_ipc_get_handle")
+        handles = self.allgather(bytes(h.raw))
+        ptrs = []
+        for r, raw in enumerate(handles):
+            if r == self._rank:
+                ptrs.append(ptr.value)
+            else:
+                q = C.c_void_p()
+                _lib.check(_lib.lib.b2_ipc_open_handle((C.c_char * 64).from_buffer_copy(raw), C.byref(q)),
+                           "b2_ipc_open_handle")
+                ptrs.append(q.value)
+        return ptr.value, ptrs
+
     @property
     def peer(self):
         """b2_peer handle: mailboxes for one-shot SCALAR all-reduces over NVLink peer memory"""

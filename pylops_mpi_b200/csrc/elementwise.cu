@@ -254,3 +254,100 @@ extern "C" int b2_fill(b2_ctx* ctx, void* out, const double v[2], size_t n, int 
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
+
+
+// ---- stationary-A MPIMatrixMult helpers (round 2) -------------------------------------------------------------
+// (1) float32 tile -> bfloat16, written to up to 8 destinations (local or IPC-mapped peer buffers): the all-gather of
+//     the X / Y panels of MatrixMult.py:663-670, 742-763 with the fp32 -> bf16 cast fused in (one read of the tile).
+// (2) out = sum over slots of the partial tiles the peers' GEMM epilogues stored here, in slot order (deterministic).
+namespace {
+struct CastDst {
+  __nv_bfloat16* p[8];
+  int n;
+};
+__global__ void __launch_bounds__(256)
+cast_multi_kernel(const float* __restrict__ src, size_t ld_src, size_t rows, size_t cols, CastDst dst, size_t ld_dst, int vec) {
+  if (vec) {
+    const size_t cv = cols / 8, total = rows * cv;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+      const size_t r = e / cv, c = (e % cv) * 8;
+      const float4 a = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+      const float4 b = *reinterpret_cast<const float4*>(src + r * ld_src + c + 4);
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+      uint4 o;
+      o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+      o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+      for (int d = 0; d < dst.n; ++d) *reinterpret_cast<uint4*>(dst.p[d] + r * ld_dst + c) = o;
+    }
+  } else {
+    const size_t total = rows * cols;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+      const size_t r = e / cols, c = e % cols;
+      const __nv_bfloat16 h = __float2bfloat16_rn(src[r * ld_src + c]);
+      for (int d = 0; d < dst.n; ++d) dst.p[d][r * ld_dst + c] = h;
+    }
+  }
+}
+__global__ void __launch_bounds__(256)
+sum_slots_kernel(const float* __restrict__ slots, size_t slot_stride, int nslots, size_t ld_in, float* __restrict__ out,
+                 size_t rows, size_t cols, int vec) {
+  if (vec) {
+    const size_t cv = cols / 4, total = rows * cv;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+      const size_t r = e / cv, c = (e % cv) * 4;
+      float4 acc = *reinterpret_cast<const float4*>(slots + r * ld_in + c);
+      for (int s = 1; s < nslots; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(slots + (size_t)s * slot_stride + r * ld_in + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(out + r * cols + c) = acc;
+    }
+  } else {
+    const size_t total = rows * cols;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+      const size_t r = e / cols, c = e % cols;
+      float acc = slots[r * ld_in + c];
+      for (int s = 1; s < nslots; ++s) acc += slots[(size_t)s * slot_stride + r * ld_in + c];
+      out[r * cols + c] = acc;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int b2_cast_bf16_multi(b2_ctx* ctx, const float* src, size_t ld_src, size_t rows, size_t cols,
+                                  void* const* dsts_host, int ndst, size_t ld_dst, void* stream) {
+  if (!ctx || ndst < 1 || ndst > 8 || !dsts_host) return B2_ERR_ARG;
+  if (rows == 0 || cols == 0) return B2_OK;
+  if (!src) return B2_ERR_ARG;
+  CastDst d;
+  d.n = ndst;
+  int vec = (cols % 8 == 0) && (ld_src % 4 == 0) && (ld_dst % 8 == 0) && b2_aligned16(src);
+  for (int i = 0; i < 8; ++i) {
+    d.p[i] = i < ndst ? (__nv_bfloat16*)dsts_host[i] : nullptr;
+    if (i < ndst && !dsts_host[i]) return B2_ERR_ARG;
+    if (i < ndst && !b2_aligned16(dsts_host[i])) vec = 0;
+  }
+  const size_t work = vec ? rows * (cols / 8) : rows * cols;
+  size_t blocks = (work + 255) / 256;
+  const size_t cap = (size_t)ctx->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  cast_multi_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld_src, rows, cols, d, ld_dst, vec);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+extern "C" int b2_sum_slots(b2_ctx* ctx, const float* slots, size_t slot_stride, int nslots, size_t ld_in, float* out,
+                            size_t rows, size_t cols, void* stream) {
+  if (!ctx || nslots < 1) return B2_ERR_ARG;
+  if (rows == 0 || cols == 0) return B2_OK;
+  if (!slots || !out) return B2_ERR_ARG;
+  const int vec = (cols % 4 == 0) && (ld_in % 4 == 0) && (slot_stride % 4 == 0) && b2_aligned16(slots) && b2_aligned16(out);
+  const size_t work = vec ? rows * (cols / 4) : rows * cols;
+  size_t blocks = (work + 255) / 256;
+  const size_t cap = (size_t)ctx->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  sum_slots_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(slots, slot_stride, nslots, ld_in, out, rows, cols, vec);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}

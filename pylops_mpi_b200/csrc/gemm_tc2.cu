@@ -144,11 +144,20 @@ __device__ __forceinline__ TileCoord tile_coord(uint32_t tile, uint32_t num_m, u
   return {first_m + in_group % gsize, in_group / gsize};
 }
 
-template <bool A_MN>
+// column-segmented output (stationary-A MPIMatrixMult, round 2): output columns [c*seg_cols, (c+1)*seg_cols) go to
+// base[c] (leading dimension ldc) -- in general a buffer in ANOTHER GPU's memory (IPC-mapped, written over NVLink
+// by the epilogue's 16-byte stores), so the reduce-scatter of the partial products needs no separate collective.
+struct SegOut {
+  float* base[8];
+  uint32_t seg_cols;     // multiple of 32
+  uint32_t nseg;         // 0 = plain C
+};
+
+template <bool A_MN, bool SEG = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      float* __restrict__ C, size_t ldc, uint32_t m, uint32_t n, uint32_t k, int accumulate,
-                     int vec_ok) {
+                     int vec_ok, const SegOut seg = SegOut{}) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -259,9 +268,18 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((g * 32u) << 16) + acc * BN + c0, v);
         tmem_ld_wait();
-        const size_t col0 = (size_t)tc.n_blk * BN + c0;
-        if (row < m && col0 < n) {
-          if (vec_ok && col0 + 32 <= n) {
+        size_t col0 = (size_t)tc.n_blk * BN + c0;
+        const bool in_range = row < m && col0 < n;
+        if constexpr (SEG) {
+          if (in_range) {      // this 32-column chunk lies inside ONE segment (seg_cols % 32 == 0)
+            const uint32_t sidx = (uint32_t)(col0 / seg.seg_cols);
+            crow = seg.base[sidx] + row * ldc;
+            col0 -= (size_t)sidx * seg.seg_cols;
+          }
+        }
+        if (in_range) {
+          const size_t nlim = SEG ? (size_t)seg.seg_cols : (size_t)n;     // SEG: n is a whole number of segments
+          if (vec_ok && col0 + 32 <= nlim) {
 #pragma unroll
             for (uint32_t j = 0; j < 32; j += 4) {
               float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
@@ -276,7 +294,7 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           } else {
 #pragma unroll
             for (uint32_t j = 0; j < 32; ++j) {
-              if (col0 + j < n) {
+              if (col0 + j < nlim) {
                 float o = __uint_as_float(v[j]);
                 if (accumulate) o += crow[col0 + j];
                 crow[col0 + j] = o;
@@ -355,6 +373,54 @@ int b2_gemm_bf16_2cta(b2_ctx* ctx, const void* A, size_t lda, const void* B, siz
     }
     gemm_bf16_tc2_kernel<false><<<2 * clusters, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, C, ldc, (uint32_t)m, (uint32_t)n,
                                                                                (uint32_t)k, accumulate, vec_ok);
+  }
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+
+// C segments: out[:, c*seg_cols:(c+1)*seg_cols) = (op(A) B)[:, same columns] written to segs_host[c] (ld = ldc);
+// n must equal nseg * seg_cols, seg_cols % 32 == 0, every segment base 16-byte aligned, ldc % 4 == 0.
+extern "C" int b2_gemm_bf16_seg(b2_ctx* ctx, const void* A, size_t lda, const void* B, size_t ldb, float* const* segs_host,
+                                int nseg, size_t seg_cols, size_t ldc, size_t m, size_t n, size_t k, int op_a, void* stream) {
+  if (!ctx || !A || !B || !segs_host || nseg < 1 || nseg > 8) return B2_ERR_ARG;
+  if (op_a != B2_OP_N && op_a != B2_OP_T && op_a != B2_OP_H) return B2_ERR_ARG;
+  if (m == 0 || n == 0 || k == 0) return B2_ERR_ARG;
+  if (seg_cols % 32 || n != (size_t)nseg * seg_cols || (ldc % 4)) return B2_ERR_ARG;
+  if (m > 0x7fffffffu || n > 0x7fffffffu || k > 0x7fffffffu) return B2_ERR_ARG;
+  if (!b2_aligned16(A) || !b2_aligned16(B) || (lda % 8) || (ldb % 8)) return B2_ERR_ALIGN;
+  SegOut so;
+  so.seg_cols = (uint32_t)seg_cols;
+  so.nseg = (uint32_t)nseg;
+  for (int i = 0; i < 8; ++i) {
+    so.base[i] = i < nseg ? segs_host[i] : nullptr;
+    if (i < nseg && (!segs_host[i] || !b2_aligned16(segs_host[i]))) return B2_ERR_ALIGN;
+  }
+  const bool a_mn = (op_a != B2_OP_N);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap tmA, tmB;
+  int rc = a_mn ? make_tmap2(&tmA, A, k, m, lda, 64, BK) : make_tmap2(&tmA, A, m, k, lda, 64, BM);
+  if (rc) return rc;
+  rc = make_tmap2(&tmB, B, k, n, ldb, 64, BK);
+  if (rc) return rc;
+  const uint32_t num_tiles = (uint32_t)(((m + 2 * BM - 1) / (2 * BM)) * ((n + BN - 1) / BN));
+  uint32_t clusters = (uint32_t)ctx->sm_count / 2;
+  if (num_tiles < clusters) clusters = num_tiles;
+  static bool attr_set[2] = {false, false};
+  if (a_mn) {
+    if (!attr_set[1]) {
+      B2_CUDA(cudaFuncSetAttribute(gemm_bf16_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+      attr_set[1] = true;
+    }
+    gemm_bf16_tc2_kernel<true, true><<<2 * clusters, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, nullptr, ldc, (uint32_t)m, (uint32_t)n,
+                                                                                    (uint32_t)k, 0, 1, so);
+  } else {
+    if (!attr_set[0]) {
+      B2_CUDA(cudaFuncSetAttribute(gemm_bf16_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+      attr_set[0] = true;
+    }
+    gemm_bf16_tc2_kernel<false, true><<<2 * clusters, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, nullptr, ldc, (uint32_t)m, (uint32_t)n,
+                                                                                     (uint32_t)k, 0, 1, so);
   }
   B2_LAUNCH_CHECK();
   return B2_OK;

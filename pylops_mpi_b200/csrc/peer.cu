@@ -33,8 +33,12 @@ __device__ __forceinline__ double ld_volatile(const double* p) {
   return v;
 }
 
+// The sequence number lives in DEVICE memory (read at entry, advanced at exit by this single-CTA kernel): a call
+// is a pure kernel launch with no host-side state, so it can be captured in a CUDA graph and replayed
+// (the CGLS iteration graph, optimization/cls_basic.py).
 __global__ void peer_allreduce_kernel(PeerPtrs pp, int rank, int P, double* __restrict__ vals, int k,
-                                      unsigned long long seq, int op) {
+                                      unsigned long long* seq_dev, int op) {
+  const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(seq_dev) + 1ull;
   const int par = (int)(seq & 1ull);
   const int t = threadIdx.x;
   if (t < P) {
@@ -57,13 +61,15 @@ __global__ void peer_allreduce_kernel(PeerPtrs pp, int rank, int P, double* __re
     }
     vals[t] = acc;
   }
+  __syncthreads();
+  if (t == 0) *reinterpret_cast<volatile unsigned long long*>(seq_dev) = seq;
 }
 }  // namespace
 
 struct b2_peer {
   int rank, size;
   PeerPtrs pp;
-  unsigned long long seq;
+  unsigned long long* seq_dev;
 };
 
 extern "C" size_t b2_peer_slots_bytes(void) { return sizeof(Slots); }
@@ -77,16 +83,19 @@ extern "C" int b2_peer_create(int rank, int size, void* const* slots_host, b2_pe
   b2_peer* h = new b2_peer();
   h->rank = rank;
   h->size = size;
-  h->seq = 0;
+  h->seq_dev = nullptr;
   for (int r = 0; r < PEER_MAX; ++r) h->pp.p[r] = r < size ? (Slots*)slots_host[r] : nullptr;
   cudaError_t e = cudaMemset(slots_host[rank], 0, sizeof(Slots));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->seq_dev, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->seq_dev, 0, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  if (e != cudaSuccess) { delete h; return (int)e; }
+  if (e != cudaSuccess) { if (h->seq_dev) cudaFree(h->seq_dev); delete h; return (int)e; }
   *out = h;
   return B2_OK;
 }
 
 extern "C" int b2_peer_destroy(b2_peer* h) {
+  if (h && h->seq_dev) cudaFree(h->seq_dev);
   delete h;
   return B2_OK;
 }
@@ -95,8 +104,7 @@ extern "C" int b2_peer_destroy(b2_peer* h) {
 extern "C" int b2_peer_allreduce(b2_peer* h, double* vals_dev, int k, int op, void* stream) {
   if (!h || !vals_dev || k < 1 || k > VAL_MAX) return B2_ERR_ARG;
   if (op != B2_SUM && op != B2_MAX && op != B2_MIN) return B2_ERR_ARG;
-  h->seq += 1;
-  peer_allreduce_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->pp, h->rank, h->size, vals_dev, k, h->seq, op);
+  peer_allreduce_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(h->pp, h->rank, h->size, vals_dev, k, h->seq_dev, op);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
@@ -127,7 +135,10 @@ __device__ __forceinline__ char* vec_slot(char* base, int par, int src) {
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-peer_allreduce_vec_kernel(VecPtrs pp, int rank, int P, T* __restrict__ buf, size_t n, unsigned long long seq) {
+peer_allreduce_vec_kernel(VecPtrs pp, int rank, int P, T* __restrict__ buf, size_t n, unsigned long long* seq_dev) {
+  // device-resident sequence number (graph-capturable): every CTA reads it before phase 1; the LAST CTA to finish
+  // phase 1 advances it -- no CTA can leave phase 2 before that (all flags depend on every rank's last arriver)
+  const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(seq_dev) + 1ull;
   const int par = (int)(seq & 1ull);
   constexpr int V = 16 / sizeof(T);
   const size_t nvec = n / V;
@@ -146,6 +157,7 @@ peer_allreduce_vec_kernel(VecPtrs pp, int rank, int P, T* __restrict__ buf, size
     const unsigned int t = atomicAdd(&me->arrive[par], 1u);
     if (t == gridDim.x - 1) {           // last CTA: everything of this rank is on its way -> publish
       me->arrive[par] = 0u;
+      *reinterpret_cast<volatile unsigned long long*>(seq_dev) = seq;
       __threadfence_system();
       for (int d = 0; d < P; ++d)
         st_release_sys(&reinterpret_cast<VecBox*>(pp.p[d])->flag[par][rank], seq);
@@ -168,7 +180,7 @@ peer_allreduce_vec_kernel(VecPtrs pp, int rank, int P, T* __restrict__ buf, size
 struct b2_peer_vec {
   int rank, size;
   VecPtrs pp;
-  unsigned long long seq;
+  unsigned long long* seq_dev;
 };
 
 extern "C" size_t b2_peer_vec_bytes(void) { return VEC_HDR_BYTES + 2 * PEER_MAX * VEC_SLOT_BYTES; }
@@ -179,15 +191,18 @@ extern "C" int b2_peer_vec_create(int rank, int size, void* const* boxes_host, b
   b2_peer_vec* h = new b2_peer_vec();
   h->rank = rank;
   h->size = size;
-  h->seq = 0;
+  h->seq_dev = nullptr;
   for (int r = 0; r < PEER_MAX; ++r) h->pp.p[r] = r < size ? (char*)boxes_host[r] : nullptr;
   cudaError_t e = cudaMemset(boxes_host[rank], 0, VEC_HDR_BYTES);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->seq_dev, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemset(h->seq_dev, 0, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  if (e != cudaSuccess) { delete h; return (int)e; }
+  if (e != cudaSuccess) { if (h->seq_dev) cudaFree(h->seq_dev); delete h; return (int)e; }
   *out = h;
   return B2_OK;
 }
 extern "C" int b2_peer_vec_destroy(b2_peer_vec* h) {
+  if (h && h->seq_dev) cudaFree(h->seq_dev);
   delete h;
   return B2_OK;
 }
@@ -199,15 +214,14 @@ extern "C" int b2_peer_vec_allreduce(b2_peer_vec* h, void* buf_dev, size_t n, in
   const size_t esz = b2_dtype_size(dtype);
   if ((dtype != B2_F32 && dtype != B2_F64) || n * esz > VEC_SLOT_BYTES) return B2_ERR_ARG;
   if (!b2_aligned16(buf_dev)) return B2_ERR_ALIGN;
-  h->seq += 1;
   // few CTAs: all of them spin on flags, so they must be co-resident (16 << 148 SMs)
   size_t work = (n * esz + 16 * 256 - 1) / (16 * 256);
   const unsigned grid = (unsigned)(work < 1 ? 1 : (work > 16 ? 16 : work));
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == B2_F32)
-    peer_allreduce_vec_kernel<float><<<grid, 256, 0, st>>>(h->pp, h->rank, h->size, (float*)buf_dev, n, h->seq);
+    peer_allreduce_vec_kernel<float><<<grid, 256, 0, st>>>(h->pp, h->rank, h->size, (float*)buf_dev, n, h->seq_dev);
   else
-    peer_allreduce_vec_kernel<double><<<grid, 256, 0, st>>>(h->pp, h->rank, h->size, (double*)buf_dev, n, h->seq);
+    peer_allreduce_vec_kernel<double><<<grid, 256, 0, st>>>(h->pp, h->rank, h->size, (double*)buf_dev, n, h->seq_dev);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }

@@ -445,3 +445,31 @@ extern "C" int b2_scalar_div(double* out_dev, const double* num_dev, const doubl
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
+
+
+// history of solver scalars kept ON THE DEVICE: hist[it * nvals + j] = |src[j * stride]|, then an optional scalar copy
+// (*copy_dst = *copy_src: kold <- k of the CGLS recurrence, cls_basic.py:397) and ++(*it).  Lets a whole block of CGLS
+// iterations run (or replay as a CUDA graph) with no host round trip; the host reads the history once per block
+// (the reference synchronises five times per iteration, cls_basic.py:389-401).
+namespace {
+__global__ void history_push_kernel(const double* src, int nvals, int stride, double* hist, unsigned long long* it,
+                                    unsigned long long cap, double* copy_dst, const double* copy_src) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const unsigned long long i = *it;
+    if (i < cap)
+      for (int j = 0; j < nvals; ++j) hist[i * (unsigned long long)nvals + j] = fabs(src[j * stride]);
+    if (copy_dst) *copy_dst = *copy_src;
+    *it = i + 1ull;
+  }
+}
+}  // namespace
+
+extern "C" int b2_history_push(const double* src_dev, int nvals, int stride, double* hist_dev, void* it_dev,
+                               size_t cap, double* copy_dst_dev, const double* copy_src_dev, void* stream) {
+  if (!src_dev || !hist_dev || !it_dev || nvals < 1 || nvals > 16 || stride < 1) return B2_ERR_ARG;
+  if ((copy_dst_dev == nullptr) != (copy_src_dev == nullptr)) return B2_ERR_ARG;
+  history_push_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(src_dev, nvals, stride, hist_dev, (unsigned long long*)it_dev,
+                                                          (unsigned long long)cap, copy_dst_dev, copy_src_dev);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}

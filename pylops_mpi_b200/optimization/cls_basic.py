@@ -44,6 +44,28 @@ class Solver:
         print("-" * nbar + "\n")
 
 
+_GRAPH_SAFE_TYPES = ("MPIBlockDiag", "MPIVStack", "MPIHStack", "MPIFirstDerivative", "MPISecondDerivative",
+                     "_MPISummaMatrixMult", "_MPIBlockMatrixMult", "_AdjointLinearOperator", "_TransposedLinearOperator",
+                     "_ProductLinearOperator", "_ScaledLinearOperator", "_SumLinearOperator", "_ConjLinearOperator",
+                     "MatrixMult", "FirstDerivative", "SecondDerivative")
+
+
+def _graph_safe(Op) -> bool:
+    """may an apply of ``Op`` be captured once in a CUDA graph and replayed?  Conservative whitelist: operators of
+    this package whose apply is a fixed sequence of kernel launches / collectives with no host-side per-call state
+    (MPIFredholm1's fused mode toggles double buffers on the host, third-party operators are unknown -> eager)"""
+    name = type(Op).__name__
+    if name not in _GRAPH_SAFE_TYPES:
+        return False
+    if name == "_MPISummaMatrixMult" and Op.base_comm.Get_size() > 1 and not getattr(Op, "_stationary", False):
+        return False       # the pipelined SUMMA forks streams per round: keep it eager
+    for child in list(getattr(Op, "args", ())) + list(getattr(Op, "ops", ())):
+        if hasattr(child, "shape") and not isinstance(child, (int, float, complex, np.number)):
+            if not _graph_safe(child):
+                return False
+    return True
+
+
 def _generic(*arrs) -> bool:
     """True when any operand is not a plain DistributedArray (StackedDistributedArray models / data,
     test_solver.py:303+): the solvers then run the reference's own sequence of ``dot / + / *`` operations
@@ -284,6 +306,9 @@ class CGLS(Solver):
         dev, st = self._dev, self._st
         QQ, CC, K, SS, XX, A_, B_, KOLD = 0, st, 4, 4 + st, 4 + 2 * st, 12, 13, 14
         sub = self.c.sub_comm
+        if getattr(self, "_q_stale", False):       # a block run (rotated order) left q one matvec behind
+            self.q = self.Op.matvec(self.c)
+            self._q_stale = False
         # a = |kold / (q.q + damp c.c)|                                                  (:389)
         _dots_device([self.q], dev, QQ)
         _dots_device([self.c], dev, CC)
@@ -312,10 +337,114 @@ class CGLS(Solver):
             self._print_step(x)
         return x
 
+    # ---- block execution: iterations without host round trips, replayed as ONE CUDA graph per iteration -----------
+    def _body(self, x, hist: torch.Tensor, it_dev: torch.Tensor):
+        """one CGLS iteration in ROTATED order (q = Op c first): every array that crosses iterations (x, s, c) is
+        updated in place and q, r live and die inside the body, so the captured graph can be replayed verbatim.
+        Same recurrences and the same kernels as :meth:`step`; the three per-iteration scalars go to ``hist``."""
+        dev, st = self._dev, self._st
+        QQ, CC, K, SS, XX, A_, B_, KOLD = 0, st, 4, 4 + st, 4 + 2 * st, 12, 13, 14
+        sub = self.c.sub_comm
+        self.q = self.Op.matvec(self.c)
+        _dots_device([self.q], dev, QQ)
+        _dots_device([self.c], dev, CC)
+        allreduce_(sub, dev[0:2 * st], "sum")
+        _scalar_div(dev, A_, dev, KOLD, dev, QQ, dev, CC, self.damp)
+        _lincomb_dev(x, dev, A_, 1.0, self.c, None, 0, 1.0, x)
+        _lincomb_dev(self.s, dev, A_, -1.0, self.q, None, 0, 1.0, self.s)
+        r = self.Op.rmatvec(self.s)
+        if self.damp != 0.0:
+            r.axpy_(-self.damp, x)
+        _dots_device([r], dev, K)
+        _dots_device([self.s], dev, SS)
+        _dots_device([x], dev, XX)
+        allreduce_(sub, dev[4:4 + 3 * st], "sum")
+        _scalar_div(dev, B_, dev, K, dev, KOLD)
+        _lincomb_dev(self.c, None, 0, 1.0, r, dev, B_, 1.0, self.c)
+        _lib.check(_lib.lib.b2_history_push(dev.data_ptr() + 8 * K, 3, st, hist.data_ptr(), it_dev.data_ptr(),
+                                            hist.shape[0], dev.data_ptr() + 8 * KOLD, dev.data_ptr() + 8 * K,
+                                            _lib.stream()), "b2_history_push")
+
+    def _run_blocks(self, x, niter: int):
+        """remaining iterations in blocks: the body is captured ONCE in a CUDA graph (after two eager warm-up
+        iterations) and replayed; the host reads the scalar history once per block.  With tol > 0 a block is at
+        most 8 iterations and is re-run from a checkpoint up to the stopping iteration, so x, cost and the
+        iteration count are exactly those of the reference's per-iteration test ``kold > tol`` (cls_basic.py:436)."""
+        import os
+        device = x.local_array.device
+        total = niter - self.iiter
+        hist = torch.zeros((total + 2, 3), dtype=torch.float64, device=device)
+        it_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        done = [0]          # iterations whose scalars are in hist
+
+        def absorb(upto: int):
+            """move hist[done:upto] to the host-side cost arrays; returns the first stop index or None"""
+            rows = hist[done[0]:upto].cpu().numpy()
+            stop = None
+            for i, (k, ss, xx) in enumerate(rows):
+                self.kold = float(k)
+                self.iiter += 1
+                self.cost.append(float(np.sqrt(ss)))
+                self.cost1.append(np.sqrt(float(self.cost[self.iiter] ** 2 + self.damp * xx)))
+                if not (self.iiter < niter and self.kold > self.tol):
+                    stop = done[0] + i + 1
+                    break
+            done[0] = upto if stop is None else stop
+            return stop
+
+        def rewind(ckpt, upto_it: int):
+            xs, ss_, cs = ckpt
+            for dst, src in ((x, xs), (self.s, ss_), (self.c, cs)):
+                dst.local_array.copy_(src)
+            self._dev[14] = self._kold_ckpt
+            it_dev.fill_(upto_it)
+
+        use_graph = os.environ.get("B2_CGLS_GRAPH", "1") != "0" and _graph_safe(self.Op)
+        state = {"graph": None, "use": use_graph, "warm": 0}
+
+        def one():
+            """one iteration: eager for the first two (lazy workspaces, communicators), then captured once and replayed"""
+            if state["graph"] is None and state["use"] and state["warm"] >= 2:
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):          # records only: nothing executes during capture
+                        self._body(x, hist, it_dev)
+                    state["graph"] = g
+                except Exception:
+                    state["use"] = False               # not capturable (host sync inside an operator ...): stay eager
+                    torch.cuda.synchronize()
+            if state["graph"] is not None:
+                state["graph"].replay()
+            else:
+                self._body(x, hist, it_dev)
+                state["warm"] += 1
+
+        block = total if self.tol <= 0.0 else min(total, 8)
+        while self.iiter < niter and self.kold > self.tol:
+            n = min(block, niter - self.iiter)
+            start = done[0]
+            ckpt = tuple(a.local_array.clone() for a in (x, self.s, self.c))
+            self._kold_ckpt = float(self.kold)
+            for _ in range(n):
+                one()
+            stop = absorb(start + n)
+            if stop is not None and stop < start + n:
+                # the stopping test fired inside the block: redo exactly the iterations up to it from the checkpoint
+                rewind(ckpt, start)
+                for _ in range(stop - start):
+                    one()
+            del ckpt
+        self._q_stale = True        # rotated order: q is one matvec behind c (and lives in the graph's memory pool)
+        self.q = None
+        return x
+
     def run(self, x, niter: Optional[int] = None, show: bool = False, itershow=(10, 10, 10)):
         niter = self.niter if niter is None else niter
         if niter is None:
             raise ValueError("niter must not be None")
+        plain_callback = type(self).callback is Solver.callback and not self.callbacks
+        if not self._gen and not show and plain_callback and niter - self.iiter > 0:
+            return self._run_blocks(x, niter)
         while self.iiter < niter and self.kold > self.tol:
             showstep = bool(show and (self.iiter < itershow[0] or niter - self.iiter < itershow[1]
                                       or self.iiter % itershow[2] == 0))

@@ -202,12 +202,9 @@ def run_all(pm, comm, full_size: bool = True):
             xt = [X[(r // Pc) * bkX:(r // Pc + 1) * bkX, (r % Pc) * bm:(r % Pc + 1) * bm] for r in range(P)]
             Yref = A @ X
             Xref = A.T @ Yref
-            for kw in ({}, {"replicate": True}, {"stationary": True}):
-                try:
-                    Aop = pm.MPIMatrixMult(A[ri * bn:(ri + 1) * bn, ci * bkA:(ci + 1) * bkA].copy(), M, kind="summa",
-                                           dtype=np.float64, grid=(Pr, Pc), **kw)
-                except TypeError:
-                    continue            # mode not built
+            for kw in ({}, {"replicate": True}):
+                Aop = pm.MPIMatrixMult(A[ri * bn:(ri + 1) * bn, ci * bkA:(ci + 1) * bkA].copy(), M, kind="summa",
+                                       dtype=np.float64, grid=(Pr, Pc), **kw)
                 xd = pm.DistributedArray(global_shape=K * M, local_shapes=[t.size for t in xt], dtype=np.float64)
                 xd[:] = xt[rank].ravel()
                 y = Aop @ xd
@@ -221,6 +218,57 @@ def run_all(pm, comm, full_size: bool = True):
                 worst = max(worst, float(det.split()[-1]))
         return True, f"grid {Pr}x{Pc}, worst {worst:.2e}"
     check("MPIMatrixMult SUMMA on the BASELINE grid (float64) vs dense", summa_rect)
+
+    # ---- bf16 -> fp32 tensor-core modes on every factorisation of P: SUMMA / replicated / stationary-A ------------
+    def summa_bf16_modes():
+        worst = 0.0
+        for (Pr, Pc) in [(g, P // g) for g in range(1, P + 1) if P % g == 0]:
+            L = Pr * Pc // math.gcd(Pr, Pc)
+            # ragged N and K (zero-padding paths) whose padded tiles stay 8-aligned; M / Pc % 32 == 0
+            N, K, M = 64 * Pr - (3 if Pr > 1 else 0), 128 * L - (5 if L > 1 else 0), 64 * Pc
+            bn, bm = math.ceil(N / Pr), math.ceil(M / Pc)
+            Kp = math.ceil(K / L) * L
+            bkA, bkX = Kp // Pc, Kp // Pr
+            A = comm.bcast(np.random.default_rng(21).standard_normal((N, K)).astype(np.float32) / 16, 0)
+            X = comm.bcast(np.random.default_rng(22).standard_normal((K, M)).astype(np.float32), 0)
+            Ab = torch.as_tensor(A).to(torch.bfloat16)
+            A64 = Ab.double().numpy()
+            Xb = torch.as_tensor(X).to(torch.bfloat16).double().numpy()
+            ri, ci = divmod(rank, Pc)
+            xt = [X[(r // Pc) * bkX:(r // Pc + 1) * bkX, (r % Pc) * bm:(r % Pc + 1) * bm] for r in range(P)]
+            Yref = A64 @ Xb
+            bound = (np.abs(A64) @ np.abs(Xb)) * K * 6e-8 + 1e-6
+            for kw in ({}, {"replicate": True}, {"stationary": True}):
+                try:
+                    Aop = pm.MPIMatrixMult(Ab[ri * bn:(ri + 1) * bn, ci * bkA:(ci + 1) * bkA].contiguous(), M,
+                                           kind="summa", dtype="bfloat16", grid=(Pr, Pc), **kw)
+                except NotImplementedError as exc:
+                    if "stationary" in kw:
+                        continue        # tile extents of this factorisation are not 8 / 32-aligned
+                    raise exc
+                xd = pm.DistributedArray(global_shape=K * M, local_shapes=[t.size for t in xt], dtype=np.float32)
+                xd[:] = xt[rank].ravel()
+                for _ in range(2):
+                    y = Aop @ xd
+                got = _host(y.local_array).reshape(-1, min(bm, M - ci * bm))
+                ref = Yref[ri * bn:(ri + 1) * bn, ci * bm:(ci + 1) * bm]
+                if got.shape != ref.shape or not np.all(np.abs(got - ref) <= bound[ri * bn:(ri + 1) * bn, ci * bm:(ci + 1) * bm]):
+                    return False, f"grid {Pr}x{Pc} {kw or 'summa'} forward"
+                worst = max(worst, float(np.abs(got - ref).max()))
+                # adjoint of the (bf16-rounded, as the operator does) forward result
+                Yb = torch.as_tensor(Yref.astype(np.float32)).to(torch.bfloat16).double().numpy()
+                yt = [Yref[(r // Pc) * bn:(r // Pc + 1) * bn, (r % Pc) * bm:(r % Pc + 1) * bm] for r in range(P)]
+                yd = pm.DistributedArray(global_shape=N * M, local_shapes=[t.size for t in yt], dtype=np.float32)
+                yd[:] = yt[rank].astype(np.float32).ravel()
+                xa = Aop.H @ yd
+                Xref = A64.T @ Yb
+                bounda = (np.abs(A64.T) @ np.abs(Yb)) * N * 6e-8 + 1e-4
+                gota = _host(xa.local_array).reshape(-1, min(bm, M - ci * bm))
+                refa = Xref[ri * bkX:(ri + 1) * bkX, ci * bm:(ci + 1) * bm]
+                if gota.shape != refa.shape or not np.all(np.abs(gota - refa) <= bounda[ri * bkX:(ri + 1) * bkX, ci * bm:(ci + 1) * bm]):
+                    return False, f"grid {Pr}x{Pc} {kw or 'summa'} adjoint"
+        return True, f"all grids of P={P}, worst abs err {worst:.2e}"
+    check("MPIMatrixMult bf16->fp32: SUMMA / replicated / stationary-A on every grid vs float64", summa_bf16_modes)
 
     # ---- Fredholm1 KAT (test_fredholm.py:36-95), SIMT, tensor-core and fused peer paths -----------------------
     def fredholm_kat():

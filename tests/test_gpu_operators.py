@@ -451,3 +451,178 @@ def test_stacked_operator_algebra(pm):
     assert it == ito
     np.testing.assert_allclose(cost, co, rtol=1e-9)
     np.testing.assert_allclose(host(xi.asarray()), xo, rtol=1e-9, atol=1e-9)
+
+
+# ---- round 2: mixed dtypes (ADVICE high), operators on promoted data, stacked CG / CGLS, tcgen05 Fredholm -------
+def test_mixed_dtype_arithmetic_promotes_like_numpy(pm):
+    """float64 +/- float32, real * complex, dot with mixed dtypes: NumPy promotion, never a reinterpreted buffer"""
+    rng = np.random.default_rng(3)
+    a64, b32 = rng.standard_normal(1001), rng.standard_normal(1001).astype(np.float32)
+    c128 = (rng.standard_normal(1001) + 1j * rng.standard_normal(1001))
+    A, B, Cc = (pm.DistributedArray.to_dist(v) for v in (a64, b32, c128))
+    for got, ref in (((A - B), a64 - b32), ((B + A), b32 + a64), ((A * B), a64 * b32), ((B * Cc), b32 * c128),
+                     ((A + Cc), a64 + c128)):
+        assert got.dtype == ref.dtype, (got.dtype, ref.dtype)
+        np.testing.assert_allclose(host(got.asarray()), ref, rtol=1e-12)
+    np.testing.assert_allclose(A.dot(B)[0], np.dot(a64, b32), rtol=1e-12)
+    A2 = A.copy()
+    A2 += B                                          # in place: keeps the left dtype (a += b)
+    assert A2.dtype == np.float64
+    np.testing.assert_allclose(host(A2.asarray()), a64 + b32, rtol=1e-12)
+    B2 = B.copy()
+    B2 -= A
+    assert B2.dtype == np.float32
+    np.testing.assert_allclose(host(B2.asarray()), (b32 - a64).astype(np.float32), rtol=1e-6)
+    with pytest.raises(TypeError):
+        A2 += Cc                                     # complex into real in place: refused, like NumPy
+    z = A * (1 + 2j)                                 # real array times complex scalar promotes
+    assert z.dtype == np.complex128
+    np.testing.assert_allclose(host(z.asarray()), a64 * (1 + 2j), rtol=1e-12)
+
+
+def test_cg_with_float64_x0_and_float32_operator(pm):
+    """the ADVICE example: default float64 x0 with a float32 operator must not mix buffers in axpy_/xpby_"""
+    n = 64
+    A = np.random.default_rng(5).standard_normal((n, n)).astype(np.float32)
+    A = A @ A.T / n + 2 * np.eye(n, dtype=np.float32)
+    Op = pm.MPIBlockDiag([pm.MatrixMult(A)])
+    xt = np.random.default_rng(6).standard_normal(n)
+    y = Op @ pm.DistributedArray.to_dist(xt.astype(np.float32))
+    x0 = pm.DistributedArray.to_dist(np.zeros(n))   # float64
+    xinv, iit, cost = pm.cg(Op, y, x0=x0, niter=40, tol=0.0)
+    np.testing.assert_allclose(host(xinv.asarray()), xt, rtol=0, atol=1e-4 * np.abs(xt).max())
+    xinv2, *_ = pm.cgls(Op, y, x0=x0, niter=60, tol=0.0)
+    np.testing.assert_allclose(host(xinv2.asarray()), xt, rtol=0, atol=1e-3 * np.abs(xt).max())
+
+
+def test_real_block_applied_to_complex_data_keeps_imaginary_part(pm):
+    """result_type(op, x): a real MatrixMult block inside a complex-typed MPIBlockDiag (ADVICE medium)"""
+    rng = np.random.default_rng(8)
+    A = rng.standard_normal((31, 17))
+    xc = rng.standard_normal(17) + 1j * rng.standard_normal(17)
+    Op = pm.MPIBlockDiag([pm.MatrixMult(A)], dtype=np.complex128)
+    y = Op @ pm.DistributedArray.to_dist(xc)
+    np.testing.assert_allclose(host(y.asarray()), A @ xc, rtol=1e-12)
+    ya = Op.H @ y
+    np.testing.assert_allclose(host(ya.asarray()), A.T @ (A @ xc), rtol=1e-12)
+    # mixed float32 / float64 blocks in one BlockDiag: output dtype = result_type of the blocks
+    B32 = rng.standard_normal((9, 5)).astype(np.float32)
+    Op2 = pm.MPIBlockDiag([pm.MatrixMult(A), pm.MatrixMult(B32)])
+    xv = rng.standard_normal(22)
+    y2 = Op2 @ pm.DistributedArray.to_dist(xv)
+    assert y2.dtype == np.float64
+    np.testing.assert_allclose(host(y2.asarray()), np.concatenate([A @ xv[:17], B32.astype(np.float64) @ xv[17:]]), rtol=1e-6)
+
+
+def test_local_operator_typeerror_is_not_swallowed(pm):
+    """a TypeError raised INSIDE an operator must propagate (out= support is detected by signature, not by catching)"""
+    class Bad(pm.local.LocalOperator):
+        shape = (4, 4)
+        dtype = np.float64
+
+        def matvec(self, x, out=None):
+            raise TypeError("genuine bug inside the operator")
+    with pytest.raises(TypeError, match="genuine bug"):
+        pm.MPIBlockDiag([Bad()]) @ pm.DistributedArray.to_dist(np.ones(4))
+
+
+def test_cg_cgls_on_stacked_arrays(pm):
+    """reference tests/test_solver.py:303-427: CG / CGLS with StackedDistributedArray models (MPIStackedBlockDiag)"""
+    rng = np.random.default_rng(11)
+    n1, n2 = 13, 7
+    A1 = rng.standard_normal((n1, n1)); A1 = A1 @ A1.T + n1 * np.eye(n1)
+    A2 = rng.standard_normal((n2, n2)); A2 = A2 @ A2.T + n2 * np.eye(n2)
+    Op = pm.MPIStackedBlockDiag([pm.MPIBlockDiag([pm.MatrixMult(A1)]), pm.MPIBlockDiag([pm.MatrixMult(A2)])])
+    x1, x2 = rng.standard_normal(n1), rng.standard_normal(n2)
+    xs = pm.StackedDistributedArray([pm.DistributedArray.to_dist(x1), pm.DistributedArray.to_dist(x2)])
+    y = Op.matvec(xs)
+    x0 = pm.StackedDistributedArray([pm.DistributedArray.to_dist(np.zeros(n1)), pm.DistributedArray.to_dist(np.zeros(n2))])
+    xcg, iit, cost = pm.cg(Op, y, x0=x0, niter=30, tol=0.0)
+    np.testing.assert_allclose(host(xcg.asarray()), np.concatenate([x1, x2]), rtol=1e-8, atol=1e-10)
+    xls, istop, iit, r1, r2, cost = pm.cgls(Op, y, x0=x0, niter=60, tol=0.0)
+    np.testing.assert_allclose(host(xls.asarray()), np.concatenate([x1, x2]), rtol=1e-6, atol=1e-8)
+    # same numbers as the oracle's CGLS on the dense block-diagonal system (the reference's own recurrences)
+    import scipy.linalg
+    Ad = scipy.linalg.block_diag(A1, A2)
+    mv = lambda a: o.SimArray([Ad @ a.locs[0]])       # noqa: E731
+    rmv = lambda a: o.SimArray([Ad.T @ a.locs[0]])    # noqa: E731
+    xo, *_r, cost_o = o.cgls(mv, rmv, o.SimArray([Ad @ np.concatenate([x1, x2])]), o.SimArray([np.zeros(n1 + n2)]), niter=10, tol=0.0)
+    xl10, *_r2, cost10 = pm.cgls(Op, y, x0=x0, niter=10, tol=0.0)
+    np.testing.assert_allclose(cost10, cost_o, rtol=1e-8)
+    np.testing.assert_allclose(host(xl10.asarray()), xo.asarray(), rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize("mode", ["h2", "b3"])
+@pytest.mark.parametrize("shape", [(21, 4, 6, 5), (5, 100, 70, 9), (2, 129, 257, 65), (3, 128, 128, 64)])
+@pytest.mark.parametrize("dtype", [np.complex64, np.float32])
+def test_fredholm1_tensor_core_path(pm, monkeypatch, mode, shape, dtype):
+    """MPIFredholm1 on tcgen05 (csrc/fredholm_tc.cu; B2_FREDHOLM_TC=1 forces it for every shape) vs the oracle in
+    complex128 / float64: 1e-5 of the largest entry per output column (north_star tolerance for complex64)"""
+    monkeypatch.setenv("B2_FREDHOLM_TC", "1")
+    monkeypatch.setenv("B2_FREDHOLM_MODE", mode)
+    nsl, nx, ny, nz = shape
+    rng = np.random.default_rng(13)
+    G = rng.standard_normal((nsl, nx, ny))
+    x = rng.standard_normal((nsl, ny, nz))
+    if dtype is np.complex64:
+        G = G + 1j * rng.standard_normal((nsl, nx, ny))
+        x = x + 1j * rng.standard_normal((nsl, ny, nz))
+    G, x = G.astype(dtype), x.astype(dtype)
+    Fr = pm.MPIFredholm1(G, nz=nz, dtype=dtype)
+    assert Fr._plan is not None
+    xd = pm.DistributedArray.to_dist(x.ravel(), partition=pm.Partition.BROADCAST)
+    wide = np.complex128 if dtype is np.complex64 else np.float64
+    refy = o.fredholm1([G.astype(wide)], x.ravel().astype(wide), nz)
+    y = Fr @ xd
+    got = host(y.local_array).reshape(nsl, nx, nz)
+    ref = refy.reshape(nsl, nx, nz)
+    assert np.all(np.abs(got - ref).max(axis=1) <= 1e-5 * np.abs(ref).max(axis=1))
+    refx = o.fredholm1([G.astype(wide)], refy, nz, adjoint=True).reshape(nsl, ny, nz)
+    gotx = host((Fr.H @ y).local_array).reshape(nsl, ny, nz)
+    assert np.all(np.abs(gotx - refx).max(axis=1) <= 2e-5 * np.abs(refx).max(axis=1))
+    assert pm.dottest(Fr, pm.DistributedArray.to_dist(x.ravel(), partition=pm.Partition.BROADCAST),
+                      pm.DistributedArray.to_dist(refy.astype(dtype), partition=pm.Partition.BROADCAST), rtol=1e-4)
+
+
+def test_fredholm1_kat_on_tensor_cores(pm, monkeypatch):
+    """tests/test_fredholm.py:36-95 arange KAT through the tcgen05 path (exactly representable inputs)"""
+    monkeypatch.setenv("B2_FREDHOLM_TC", "1")
+    for nz in (5, 1):
+        for dtype in (np.float32, np.complex64):
+            cx = dtype is np.complex64
+            G = np.arange(21 * 4 * 6, dtype=np.float64).reshape(21, 4, 6)
+            G = (G - 1j * G) if cx else G
+            xv = (np.ones((21, 6, nz)) + (1j if cx else 0))
+            Fr = pm.MPIFredholm1(G.astype(dtype), nz=nz, dtype=dtype)
+            y = Fr @ pm.DistributedArray.to_dist(xv.ravel().astype(dtype), partition=pm.Partition.BROADCAST)
+            refy = o.fredholm1([G], xv.ravel().astype(G.dtype), nz)
+            np.testing.assert_allclose(host(y.local_array), refy, rtol=1e-5)
+            np.testing.assert_allclose(host((Fr.H @ y).local_array), o.fredholm1([G], refy, nz, adjoint=True), rtol=1e-4)
+
+
+def test_fredholm1_baseline_size_complex64_vs_complex128(pm):
+    """SURVEY 8(d) C5 at full per-GPU size: 64 slices of 256 x 256 x 64 complex64 vs complex128, 1e-5 of max"""
+    nsl, ns, nr, nv = 64, 256, 256, 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    G = torch.randn(nsl, ns, nr, device="cuda", dtype=torch.complex64, generator=g)
+    xm = torch.randn(nsl * nr * nv, device="cuda", dtype=torch.complex64, generator=g)
+    Fr = pm.MPIFredholm1(G, nz=nv, dtype=np.complex64)
+    assert Fr._plan is not None          # the tensor-core path is the default at this size
+    xd = pm.DistributedArray(global_shape=xm.numel(), partition=pm.Partition.BROADCAST, dtype=np.complex64)
+    xd.local_array.copy_(xm)
+    y = Fr @ xd
+    ref = torch.matmul(G.to(torch.complex128), xm.view(nsl, nr, nv).to(torch.complex128))
+    got = y.local_array.view(nsl, ns, nv).to(torch.complex128)
+    assert ((got - ref).abs().amax(dim=1) <= 1e-5 * ref.abs().amax(dim=1)).all()
+    ya = Fr.H @ y
+    refa = torch.matmul(G.to(torch.complex128).conj().transpose(1, 2), got)
+    gota = ya.local_array.view(nsl, nr, nv).to(torch.complex128)
+    assert ((gota - refa).abs().amax(dim=1) <= 1e-5 * refa.abs().amax(dim=1)).all()
+
+
+def test_parity_check_set_runs_clean_on_one_rank(pm):
+    """the driver-visible parity set of bench.py (tests/parity_checks.py) at world size 1"""
+    import parity_checks
+    res = parity_checks.run_all(pm, pm.get_comm_world(), full_size=True)
+    assert res["failed"] == 0, res["failures"]
+    assert res["checked"] >= 10
