@@ -237,6 +237,28 @@ def time_loop(fn, steps, warmup, comm=None):
     return ms
 
 
+def numa_bind_to_gpu(dev: int):
+    """pin this process (and, by first touch, its pinned host buffers) to the NUMA node the GPU hangs off:
+    with 8 ranks the e2e host<->device pipelines otherwise cross the inter-socket link for half of the GPUs"""
+    try:
+        import torch
+        prop = torch.cuda.get_device_properties(dev)
+        bus = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"numa_node": None, "pci": bus}
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus_bound": len(cpus), "pci": bus}
+    except Exception as exc:
+        return {"numa_node": None, "error": repr(exc)[:120]}
+
+
 def run_gpu_arm(args):
     import torch
     import pylops_mpi_b200 as pm
@@ -244,6 +266,7 @@ def run_gpu_arm(args):
 
     comm = pm.get_comm_world()
     rank, size = comm.Get_rank(), comm.Get_size()
+    numa = numa_bind_to_gpu(torch.cuda.current_device())
     if size != args.gpus and rank == 0:
         print(f"warning: --gpus {args.gpus} but world size {size}", file=sys.stderr)
     peaks, peak_kind = load_peaks()
@@ -363,6 +386,7 @@ def run_gpu_arm(args):
            "d2h_bytes_per_step": nloc * row_bytes * size, "steps": e2e_steps,
            "per_gpu_pcie_GB/s_each_way": nloc * row_bytes * e2e_steps / e2e_s / 1e9,
            "api": "b2_first_derivative_host (pinned host in/out, 3-stream chunk pipeline)",
+           "numa": numa, "limiter": "PCIe (H2D + D2H of every byte; the kernel itself runs at the HBM roofline)",
            "check_vs_device_path": {"rows": nchk, "max_abs_diff": e2e_diff, "equal": e2e_diff == 0.0}}
     del xh, yh, xd, yd
 
@@ -643,6 +667,44 @@ def run_extras(pm, L, comm, peaks, args):
         out["fredholm1_fused_peer_c64_64x256x256x64_per_gpu"] = {
             "GF/s": fl * K / (ms * 1e-3) / 1e9, "us": ms / K * 1e3,
             "mode": "ONE kernel: product + all-gather via P2P stores into IPC-mapped peer buffers"}
+    # --- MDD (tutorials/mdd.py:108-120, 190-194 shapes): MPIMDC + 50 CGLS iterations, ns = nr = 256, nt = 1024
+    #     (one-sided: nfft = 513, 512 slices in the band at 8 GPUs = 64 per GPU), nv = 64, float32 / complex64 -------
+    try:
+        import warnings
+        nt, nf_loc = 1024, 64
+        gen = torch.Generator(device="cuda").manual_seed(5)
+        gt = torch.randn(nt, ns, nr, device="cuda", generator=gen) * 0.05          # real kernels -> physical spectrum
+        Gf = torch.fft.rfft(gt, n=nt, dim=0)[rank * nf_loc:(rank + 1) * nf_loc].contiguous()
+        del gt
+        mm = pm.DistributedArray(global_shape=nt * nr * nv, partition=pm.Partition.BROADCAST, dtype=np.float32)
+        mm.local_array.copy_(torch.randn(nt * nr * nv, device="cuda", generator=torch.Generator(device="cuda").manual_seed(6)))
+        res = {}
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sols = {}
+            for dom in ("time", "frequency"):
+                Mop = pm.MPIMDC(Gf, nt=nt, nv=nv, nfreq=nf_loc * size, dt=0.004, dr=1.0, twosided=False, data_domain=dom)
+                dd = Mop @ mm
+                x0 = mm.zeros_like()
+                pm.cgls(Mop, dd, x0=x0, niter=2, tol=0.0)
+                torch.cuda.synchronize()
+                comm.Barrier()
+                t0 = time.perf_counter()
+                xinv, istop, iit, r1, r2, cost = pm.cgls(Mop, dd, x0=x0, niter=50, tol=0.0)
+                torch.cuda.synchronize()
+                dt_s = time.perf_counter() - t0
+                if size > 1:
+                    dt_s = comm.allreduce(dt_s, "max")
+                sols[dom] = xinv
+                res[dom] = {"ms_per_iter": dt_s / 50 * 1e3, "iterations": int(iit), "cost_first": float(cost[0]),
+                            "cost_last": float(cost[-1]), "rel_err_vs_m_true": float((xinv - mm).norm()[0] / mm.norm()[0]),
+                            "allgathers_per_iteration": 2 if dom == "time" else 1}
+                del Mop, dd
+            res["iterates_agree_rel"] = float((sols["time"] - sols["frequency"]).norm()[0] / sols["time"].norm()[0])
+        res["config"] = f"ns=nr=256, nt={nt} one-sided, nv=64, {nf_loc} frequency slices per GPU, float32/complex64, cgls 50 it"
+        out["mdd_cgls50"] = res
+    except Exception as exc:
+        out["mdd_cgls50"] = {"error": repr(exc)[:300]}
     return out
 
 

@@ -83,6 +83,11 @@ int b2_dot(b2_ctx* ctx, const void* x, const void* y, size_t n, int dtype, int c
 /* out_dev[0] = local partial for the requested norm kind (p only for SUM_POW) */
 int b2_norm_partial(b2_ctx* ctx, const void* x, size_t n, int dtype, int kind, double p,
                     double* out_dev, void* stream);
+/* axis-wise variant (DistributedArray.norm(ord, axis=...), DistributedArray.py:688-758, 796-807): x is the local block
+ * viewed as [n_outer][n_axis][n_inner]; out_dev[o * n_inner + i] = float64 partial over the middle axis for the same
+ * norm kinds (the caller combines partials across ranks when the axis is the partition axis and takes the root) */
+int b2_norm_axis(b2_ctx* ctx, const void* x, size_t n_outer, size_t n_axis, size_t n_inner, int dtype, int kind,
+                 double p, double* out_dev, void* stream);
 /* k dot products <x_j, y_j> in ONE launch: out_dev[0..k) for real dtypes, out_dev[0..2k) as
  * (re, im) pairs for complex dtypes (CGLS needs q.q and c.c
  * together, r.r / s.s / x.x together -- cls_basic.py:389, 394-401) */

@@ -55,6 +55,9 @@ def local_split(global_shape: Tuple, base_comm, partition: Partition, axis: int)
     return tuple(local_shape)
 
 
+_KERNEL_DTYPES = (torch.float32, torch.float64, torch.complex64, torch.complex128)
+
+
 def subcomm_split(mask, comm=COMM_WORLD):
     """DistributedArray.py:74-100 (cached: one Split per distinct mask)."""
     return resolve(comm).split_by_mask(mask)
@@ -314,22 +317,41 @@ class DistributedArray(DistributedMixIn):
         return a if a.is_contiguous() else a.contiguous()
 
     def _pair(self, other: "DistributedArray") -> Tuple[torch.Tensor, torch.Tensor]:
-        """contiguous local buffers of ``self`` and ``other`` in their COMMON dtype (NumPy type promotion, as
-        the reference's ``self[:] + other[:]`` does): the single-dtype kernels must never see mixed buffers"""
+        """contiguous local buffers of ``self`` and ``other`` in their COMMON dtype (the NumPy promotion of the
+        reference's ``self.local_array + other.local_array``): the single-dtype kernels never see mixed buffers"""
         x, y = self._cont(), other._cont()
         if x.dtype != y.dtype:
             dt = torch.promote_types(x.dtype, y.dtype)
             x, y = x.to(dt), y.to(dt)
         return x, y
 
+    def _mine_from(self, out: torch.Tensor) -> "DistributedArray":
+        """wrap a result computed in the promoted dtype as an array of THIS array's dtype: the reference allocates
+        every binary-op result with ``dtype=self.dtype`` and assigns the NumPy-promoted expression into it
+        (DistributedArray.py:603-652), i.e. float32 + float64 -> float32, real + complex -> real (+ ComplexWarning)"""
+        if out.dtype != self._tdtype:
+            if out.dtype.is_complex and not self._tdtype.is_complex:
+                import warnings
+                warnings.warn("Casting complex values to real discards the imaginary part",
+                              np.exceptions.ComplexWarning, stacklevel=3)
+                out = out.real
+            out = out.to(self._tdtype).contiguous()
+        return self._like(out)
+
     def _as_mine(self, other: "DistributedArray") -> torch.Tensor:
-        """``other``'s contiguous buffer cast to THIS array's dtype (in-place updates keep the left operand's
-        dtype, like NumPy's ``a += b``; complex into real is refused as NumPy refuses it)"""
+        """``other``'s contiguous buffer cast to THIS array's dtype.  In-place updates keep the left operand's
+        dtype: the reference writes them as ``self[:] = self.local_array + other.local_array``
+        (DistributedArray.py:591-592), i.e. a NumPy ``__setitem__`` cast -- complex into real DISCARDS the imaginary
+        part with a ComplexWarning (this is what lets a real model be updated with the complex-typed, zero-imaginary
+        output of ``MDCop.H`` in CGLS, tutorials/mdd.py:190-194)."""
         y = other._cont()
         if y.dtype != self._tdtype:
             if y.dtype.is_complex and not self._tdtype.is_complex:
-                raise TypeError(f"cannot cast {y.dtype} to {self._tdtype} in an in-place update")
-            y = y.to(self._tdtype)
+                import warnings
+                warnings.warn("Casting complex values to real discards the imaginary part",
+                              np.exceptions.ComplexWarning, stacklevel=3)
+                y = y.real
+            y = y.to(self._tdtype).contiguous()
         return y
 
     def _lincomb(self, a, x: torch.Tensor, b=None, y: Optional[torch.Tensor] = None,
@@ -362,8 +384,7 @@ class DistributedArray(DistributedMixIn):
         self._check_partition_shape(x)
         self._check_mask(x)
         a, b = self._pair(x)
-        out = self._lincomb(1.0, a, -1.0, b)
-        return self._like(out, dtype=out.dtype)
+        return self._mine_from(self._lincomb(1.0, a, -1.0, b))
 
     def __isub__(self, x):
         self._check_partition_shape(x)
@@ -384,8 +405,7 @@ class DistributedArray(DistributedMixIn):
         self._check_partition_shape(dist_array)
         self._check_mask(dist_array)
         a, b = self._pair(dist_array)
-        out = self._lincomb(1.0, a, 1.0, b)
-        return self._like(out, dtype=out.dtype)
+        return self._mine_from(self._lincomb(1.0, a, 1.0, b))
 
     def iadd(self, dist_array):
         self._check_partition_shape(dist_array)
@@ -405,14 +425,13 @@ class DistributedArray(DistributedMixIn):
             if x.numel():
                 _lib.check(_lib.lib.b2_mul(_lib.ctx(), out.data_ptr(), x.data_ptr(), y.data_ptr(),
                                            x.numel(), _lib.code(x.dtype), 0, _lib.stream()), "b2_mul")
-            return self._like(out, dtype=out.dtype)
+            return self._mine_from(out)
         scalar = complex(dist_array)
         x = self._cont()
         if scalar.imag != 0.0 and not self._tdtype.is_complex:
-            # NumPy promotes real * complex scalar to the matching complex dtype
+            # the product is formed in the matching complex dtype, then assigned into a self.dtype array
             x = x.to(torch.complex64 if self._tdtype in (torch.float32, torch.bfloat16) else torch.complex128)
-        out = self._lincomb(scalar, x)
-        return self._like(out, dtype=out.dtype)
+        return self._mine_from(self._lincomb(scalar, x))
 
     # fused updates used by the solvers (no temporaries): self <- self + a*x ; self <- x + b*self
     def axpy_(self, a, x: "DistributedArray"):
@@ -495,24 +514,47 @@ class DistributedArray(DistributedMixIn):
                    "b2_norm_partial")
         return allreduce_(self._sub_comm, out, op), root
 
-    def _compute_vector_norm(self, local_array, axis: int, ord=None):
-        """axis-wise variant (DistributedArray.py:688-758) for arrays partitioned along
-        ``axis``; rarely on the hot path -> expressed with the collective + torch reductions."""
+    @staticmethod
+    def _norm_kind(ord):
         ord = 2 if ord is None else ord
         if ord in ("fro", "nuc"):
             raise ValueError(f"norm-{ord} not possible for vectors")
-        a = local_array
         if ord == 0:
-            part = torch.count_nonzero(a, dim=axis).to(torch.float64)
-            return allreduce_(self._sub_comm, part.contiguous(), SUM)
+            return _lib.NRM_COUNT_NONZERO, SUM, 0.0, 1.0
         if ord == np.inf:
-            part = a.abs().amax(dim=axis).to(torch.float64)
-            return allreduce_(self._sub_comm, part.contiguous(), MAX)
+            return _lib.NRM_MAX_ABS, MAX, 0.0, 1.0
         if ord == -np.inf:
-            part = a.abs().amin(dim=axis).to(torch.float64)
-            return allreduce_(self._sub_comm, part.contiguous(), MIN)
-        part = a.abs().to(torch.float64).pow(ord).sum(dim=axis)
-        return allreduce_(self._sub_comm, part.contiguous(), SUM).pow(1.0 / ord)
+            return _lib.NRM_MIN_ABS, MIN, 0.0, 1.0
+        if ord == 1:
+            return _lib.NRM_SUM_ABS, SUM, 1.0, 1.0
+        if ord == 2:
+            return _lib.NRM_SUM_SQ, SUM, 2.0, 0.5
+        return _lib.NRM_SUM_POW, SUM, float(ord), 1.0 / float(ord)
+
+    @staticmethod
+    def _axis_partials(a: torch.Tensor, axis: int, kind: int, p: float) -> torch.Tensor:
+        """float64 partials of the norm along ``axis`` of the local block (b2_norm_axis; no eager torch pass)"""
+        a = a if a.is_contiguous() else a.contiguous()
+        shp = tuple(a.shape)
+        n_outer = int(np.prod(shp[:axis])) if axis else 1
+        n_axis = int(shp[axis])
+        n_inner = int(np.prod(shp[axis + 1:])) if axis + 1 < len(shp) else 1
+        out = torch.empty(shp[:axis] + shp[axis + 1:], dtype=torch.float64, device=a.device)
+        if out.numel():
+            if n_axis == 0:
+                out.fill_(float("inf") if kind == _lib.NRM_MIN_ABS else 0.0)
+            else:
+                _lib.check(_lib.lib.b2_norm_axis(_lib.ctx(), a.data_ptr(), n_outer, n_axis, n_inner, _lib.code(a.dtype),
+                                                 kind, p, out.data_ptr(), _lib.stream()), "b2_norm_axis")
+        return out
+
+    def _compute_vector_norm(self, local_array, axis: int, ord=None):
+        """axis-wise variant (DistributedArray.py:688-758) for arrays partitioned along ``axis``: per-column
+        float64 partials on the device (b2_norm_axis), one Allreduce of the partial vector, root on the device"""
+        kind, op, p, root = self._norm_kind(ord)
+        part = self._axis_partials(local_array, axis, kind, p)
+        red = allreduce_(self._sub_comm, part.contiguous(), op)
+        return red.pow(root) if root != 1.0 else red
 
     def norm(self, ord=None, axis: Optional[int] = None):
         """Distributed vector norm (DistributedArray.py:774-807); float64 result
@@ -530,8 +572,10 @@ class DistributedArray(DistributedMixIn):
             x = self
         if self.axis != axis:
             norm_axis = self.axis - 1 if axis < self.axis else self.axis
-            loc = torch.linalg.vector_norm(x.local_array.to(torch.float64) if not x._tdtype.is_complex
-                                           else x.local_array, ord=2 if ord is None else ord, dim=axis)
+            kind, _op, p, root = self._norm_kind(ord)
+            loc = self._axis_partials(x.local_array, axis, kind, p)       # the whole axis is local: take the root here
+            if root != 1.0:
+                loc = loc.pow(root)
             parts = self._allgather(self._base_comm, None, loc.contiguous())
             return torch.cat(parts, dim=norm_axis)
         return x._compute_vector_norm(x.local_array, axis=axis, ord=ord)
@@ -540,7 +584,12 @@ class DistributedArray(DistributedMixIn):
     def zeros_like(self):
         """note: like the reference (:763-770) the mask is NOT propagated"""
         arr = self._like(mask=None)
-        arr._local_array.zero_()
+        n = arr._local_array.numel()
+        if self._tdtype not in _KERNEL_DTYPES:      # integer / bf16 arrays: plain memset
+            arr._local_array.zero_()
+        elif n:
+            _lib.check(_lib.lib.b2_fill(_lib.ctx(), arr._local_array.data_ptr(), _lib.cpair(0.0), n,
+                                        _lib.code(self._tdtype), _lib.stream()), "b2_fill")
         return arr
 
     def conj(self):
@@ -549,7 +598,9 @@ class DistributedArray(DistributedMixIn):
         return self._like(self._lincomb(1.0, self._cont(), conj_x=True))
 
     def copy(self):
-        return self._like(self._local_array.clone(memory_format=torch.contiguous_format))
+        if self._tdtype not in _KERNEL_DTYPES:
+            return self._like(self._local_array.clone(memory_format=torch.contiguous_format))
+        return self._like(self._lincomb(1.0, self._cont()))      # one b2_lincomb pass (out = 1 * x)
 
     def ravel(self, order: Optional[str] = "C"):
         if order != "C":

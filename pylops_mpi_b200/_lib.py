@@ -75,6 +75,7 @@ def _load():
         "b2_fill": ([vp, vp, dp, sz, i, vp], i),
         "b2_dot": ([vp, vp, vp, sz, i, i, vp, vp], i),
         "b2_norm_partial": ([vp, vp, sz, i, i, d, vp, vp], i),
+        "b2_norm_axis": ([vp, vp, sz, sz, sz, i, i, d, vp, vp], i),
         "b2_dot_multi": ([vp, i, C.POINTER(vp), C.POINTER(vp), sz, i, i, vp, vp], i),
         "b2_scalar_div": ([vp, vp, vp, vp, d, vp], i),
         "b2_history_push": ([vp, i, i, vp, vp, sz, vp, vp, vp], i),

@@ -60,7 +60,7 @@ class MPIVStack(MPILinearOperator):
                 tmp = oper.rmatvec(xi)
                 if tmp.dtype != acc.dtype:        # mixed-dtype stack: accumulate in the operator's result dtype
                     if tmp.dtype.is_complex and not acc.dtype.is_complex:
-                        raise TypeError(f"cannot accumulate {tmp.dtype} into a {acc.dtype} model")
+                        tmp = tmp.real            # NumPy __setitem__ cast of the reference (VStack.py:144-145)
                     tmp = tmp.to(acc.dtype)
                 y._lincomb(1.0, tmp.reshape(-1).contiguous(), 1.0, acc, out=acc)
         if len(self.ops) == 0:

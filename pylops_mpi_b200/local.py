@@ -47,9 +47,13 @@ def apply_into(oper, x: torch.Tensor, out: torch.Tensor, adjoint: bool) -> None:
 
 
 def _store(out: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-    """out <- y with NumPy-style same-kind casting (complex into real is refused, not silently truncated)"""
+    """out <- y with NumPy ``__setitem__`` casting, as the reference's ``y[a:b] = oper.matvec(...)``
+    (BlockDiag.py:127-129): complex into real keeps the real part and warns"""
     if y.dtype.is_complex and not out.dtype.is_complex:
-        raise TypeError(f"cannot store a {y.dtype} result into a {out.dtype} output")
+        import warnings
+        warnings.warn("Casting complex values to real discards the imaginary part", np.exceptions.ComplexWarning,
+                      stacklevel=3)
+        y = y.real
     out.copy_(y.reshape(out.shape))
     return out
 
@@ -240,6 +244,26 @@ class FFT(LocalOperator):
         s[self.axis] = slice(lo, hi)
         return tuple(s)
 
+    def _scale_band(self, out: torch.Tensor, src: torch.Tensor, a: float):
+        """out = src with the positive-frequency band (bins 1 .. npos along ``axis``) scaled by ``a`` -- through
+        b2_lincomb (copy + in-band scale: at most three launches, no eager torch elementwise pass)"""
+        one = _lib.cpair(1.0)
+        code = _lib.code(src.dtype)
+        ctx, st = _lib.ctx(), _lib.stream()
+        if self.axis == 0 and self._npos > 0 and src.is_contiguous():
+            inner = int(np.prod(self.dimsd[1:])) if len(self.dimsd) > 1 else 1
+            so, ss = out.reshape(-1), src.reshape(-1)
+            lo, hi = inner, (1 + self._npos) * inner
+            for b, e, coef in ((0, lo, 1.0), (lo, hi, a), (hi, ss.numel(), 1.0)):
+                if e > b and (coef != 1.0 or so.data_ptr() != ss.data_ptr()):
+                    _lib.check(_lib.lib.b2_lincomb(ctx, so[b:].data_ptr(), _lib.cpair(coef), ss[b:].data_ptr(), None, None,
+                                                   e - b, code, 0, st), "b2_lincomb")
+            return out
+        if out.data_ptr() != src.data_ptr():
+            out.copy_(src)
+        out[self._sl(1, 1 + self._npos)] *= a
+        return out
+
     def _matvec(self, x: torch.Tensor) -> torch.Tensor:
         x = x.reshape(self.dims)
         x = x.real if x.is_complex() else x
@@ -247,13 +271,15 @@ class FFT(LocalOperator):
         if self.ifftshift_before:
             x = torch.fft.ifftshift(x, dim=self.axis)
         y = torch.fft.rfft(x, n=self.nfft, dim=self.axis, norm="ortho")
-        y[self._sl(1, 1 + self._npos)] *= np.sqrt(2.0)
-        return y.reshape(-1)
+        return self._scale_band(y, y, float(np.sqrt(2.0))).reshape(-1)
 
     def _rmatvec(self, x: torch.Tensor) -> torch.Tensor:
-        x = x.reshape(self.dimsd).to(self.cdtype).clone()
-        x[self._sl(1, 1 + self._npos)] /= np.sqrt(2.0)
-        y = torch.fft.irfft(x, n=self.nfft, dim=self.axis, norm="ortho")
+        x = x.reshape(self.dimsd)
+        if x.dtype != self.cdtype:
+            x = x.to(self.cdtype)
+        xs = self._scale_band(torch.empty_like(x, memory_format=torch.contiguous_format), x.contiguous(),
+                              float(1.0 / np.sqrt(2.0)))
+        y = torch.fft.irfft(xs, n=self.nfft, dim=self.axis, norm="ortho")
         if self.ifftshift_before:
             y = torch.fft.fftshift(y, dim=self.axis)
         return y.reshape(-1)
@@ -268,18 +294,23 @@ class Identity(LocalOperator):
         self.shape = (int(N), int(M))
         self.dtype = _lib.numpy_dtype(_lib.torch_dtype(dtype))
 
+    @staticmethod
+    def _pad(x: torch.Tensor, n: int) -> torch.Tensor:
+        """zero-padded copy of flat ``x`` to ``n`` elements: b2_lincomb (copy) + b2_fill (tail)"""
+        x = x.reshape(-1).contiguous()
+        y = torch.empty(n, dtype=x.dtype, device=x.device)
+        code, ctx, st = _lib.code(x.dtype), _lib.ctx(), _lib.stream()
+        if x.numel():
+            _lib.check(_lib.lib.b2_lincomb(ctx, y.data_ptr(), _lib.cpair(1.0), x.data_ptr(), None, None, x.numel(), code, 0, st),
+                       "b2_lincomb")
+        if n > x.numel():
+            _lib.check(_lib.lib.b2_fill(ctx, y[x.numel():].data_ptr(), _lib.cpair(0.0), n - x.numel(), code, st), "b2_fill")
+        return y
+
     def _matvec(self, x: torch.Tensor) -> torch.Tensor:
         N, M = self.shape
-        if N <= M:
-            return x[:N]
-        y = torch.zeros(N, dtype=x.dtype, device=x.device)
-        y[:M] = x
-        return y
+        return x[:N] if N <= M else self._pad(x, N)
 
     def _rmatvec(self, x: torch.Tensor) -> torch.Tensor:
         N, M = self.shape
-        if M <= N:
-            return x[:M]
-        y = torch.zeros(M, dtype=x.dtype, device=x.device)
-        y[:N] = x
-        return y
+        return x[:M] if M <= N else self._pad(x, M)

@@ -17,8 +17,12 @@ from ..LinearOperator import MPILinearOperator
 
 class MPIFredholm1(MPILinearOperator):
     def __init__(self, G, nz: int = 1, saveGt: bool = False, usematmul: bool = True,
-                 base_comm=COMM_WORLD, dtype="float64", fused=None) -> None:
+                 base_comm=COMM_WORLD, dtype="float64", fused=None, scatter_data: bool = False) -> None:
         base_comm = resolve(base_comm)
+        # scatter_data=True (extension used by the frequency-domain MDC, waveeqprocessing/MDC.py): the DATA side stays
+        # partitioned by slices -- forward takes the BROADCAST model and returns a SCATTER array holding only this rank's
+        # slices (NO Allgather), the adjoint takes that SCATTER array and gathers the BROADCAST model.
+        self._scatter_data = bool(scatter_data)
         self.nz = int(nz)
         if not isinstance(G, torch.Tensor):
             G = torch.as_tensor(np.asarray(G))
@@ -47,7 +51,7 @@ class MPIFredholm1(MPILinearOperator):
         # fused=None (default): on when CUDA IPC peer mapping works between the ranks (probed by comm.peer)
         if fused is None:
             fused = base_comm.Get_size() > 1 and base_comm.peer is not None
-        self._fused = bool(fused) and base_comm.Get_size() > 1
+        self._fused = bool(fused) and base_comm.Get_size() > 1 and not self._scatter_data
         if self._fused:
             self._setup_arenas(base_comm)
         # tensor-core plan (csrc/fredholm_tc.cu): float32 / complex64 products run on tcgen05 with bf16x3 split
@@ -131,7 +135,54 @@ class MPIFredholm1(MPILinearOperator):
                                        _lib.code(self._tdtype), 0, _lib.stream()), "b2_lincomb")
         return y
 
+    def _local_product(self, xs: torch.Tensor, yout: torch.Tensor, adjoint: bool):
+        """this rank's slices: yout = op(G) xs (tensor-core plan when built, SIMT kernel otherwise)"""
+        if self._plan is not None:
+            _lib.check(_lib.lib.b2_fredholm_apply(self._plan, xs.data_ptr(), yout.data_ptr(), None, 0, int(adjoint),
+                                                  _lib.stream()), "b2_fredholm_apply")
+        else:
+            _lib.check(_lib.lib.b2_batched_gemm(_lib.ctx(), self.G.data_ptr(), xs.data_ptr(), yout.data_ptr(), self.nsl,
+                                                self.nx, self.ny, self.nz, int(adjoint), _lib.code(self._tdtype),
+                                                _lib.stream()), "b2_batched_gemm")
+
+    def _apply_scatter(self, x: DistributedArray, adjoint: bool) -> DistributedArray:
+        rank = self.rank
+        if not adjoint:
+            if x.partition not in [Partition.BROADCAST, Partition.UNSAFE_BROADCAST]:
+                raise ValueError(f"x should have partition={Partition.BROADCAST},{Partition.UNSAFE_BROADCAST}"
+                                 f"Got  {x.partition} instead...")
+            per = self.ny * self.nz
+            xl = x.local_array if x.local_array.dtype == self._tdtype else x.local_array.to(self._tdtype)
+            xs = xl.reshape(-1)[self.islstart[rank] * per: self.islend[rank] * per]
+            y = DistributedArray(global_shape=self.shape[0], base_comm=x.base_comm, partition=Partition.SCATTER,
+                                 local_shapes=[(int(n) * self.nx * self.nz,) for n in self.nsls], dtype=self._tdtype)
+            if self.nsl:
+                self._local_product(xs, y.local_array, False)
+            return y
+        if x.partition is not Partition.SCATTER:
+            raise ValueError(f"x should have partition={Partition.SCATTER} Got {x.partition} instead...")
+        xl = x.local_array if x.local_array.dtype == self._tdtype else x.local_array.to(self._tdtype)
+        if xl.numel() != self.nsl * self.nx * self.nz:
+            raise ValueError("scattered data does not match this rank's slices")
+        pout = self.ny * self.nz
+        y = DistributedArray(global_shape=self.shape[1], base_comm=x.base_comm, partition=Partition.BROADCAST,
+                             dtype=self._tdtype)
+        yflat = y.local_array.view(-1)
+        mine = yflat[self.islstart[rank] * pout: self.islend[rank] * pout]
+        if self.nsl:
+            self._local_product(xl.reshape(-1), mine, True)
+        if x.size > 1:
+            import ctypes as C
+            comm = x.base_comm
+            counts = (C.c_size_t * comm.size)(*[int(n) * pout for n in self.nsls])
+            offs = (C.c_size_t * comm.size)(*[int(o) * pout for o in self.islstart])
+            _lib.check(_lib.lib.b2_allgatherv_at(comm.nccl, mine.data_ptr(), yflat.data_ptr(), counts, offs,
+                                                 _lib.code(self._tdtype), _lib.stream()), "b2_allgatherv_at")
+        return y
+
     def _apply(self, x: DistributedArray, adjoint: bool) -> DistributedArray:
+        if self._scatter_data:
+            return self._apply_scatter(x, adjoint)
         if x.partition not in [Partition.BROADCAST, Partition.UNSAFE_BROADCAST]:
             raise ValueError(f"x should have partition={Partition.BROADCAST},{Partition.UNSAFE_BROADCAST}"
                              f"Got  {x.partition} instead...")

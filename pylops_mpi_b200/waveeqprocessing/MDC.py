@@ -21,9 +21,18 @@ from ..signalprocessing.Fredholm1 import MPIFredholm1
 
 def MPIMDC(G, nt: int, nv: int, nfreq: int, dt: float = 1.0, dr: float = 1.0, twosided: bool = True,
            fftengine: str = "numpy", saveGt: bool = True, conj: bool = False, usematmul: bool = False,
-           prescaled: bool = False, base_comm=COMM_WORLD):
+           prescaled: bool = False, base_comm=COMM_WORLD, data_domain: str = "time"):
     """Same signature as the reference (MDC.py:77-90); ``G`` is this rank's batch of frequency slices
-    ``(nfreq_rank, ns, nr)`` (complex); ``fftengine`` is accepted and ignored."""
+    ``(nfreq_rank, ns, nr)`` (complex); ``fftengine`` is accepted and ignored.
+
+    ``data_domain="frequency"`` (extension): the operator stops after the Fredholm stage,
+    ``Fredholm1 I F`` -- the data side is the band-limited SPECTRUM, kept SCATTERed over the ranks by frequency
+    slice.  The forward apply then needs NO Allgather at all and the adjoint a single one (of the model-side
+    spectrum), instead of one 64 MiB gather in each direction.  Because ``F1^H I1^H`` has orthonormal columns for
+    physical kernels (real DC slice), CGLS on ``|| I1 F1 d - Fredholm1 I F m ||`` produces the same iterates as on
+    the time-domain residual; :func:`mdc_data_to_frequency` maps the time-domain data once."""
+    if data_domain not in ("time", "frequency"):
+        raise ValueError("data_domain must be 'time' or 'frequency'")
     if twosided and nt % 2 == 0:
         raise ValueError('nt must be odd number')
     if not isinstance(G, torch.Tensor):
@@ -32,7 +41,9 @@ def MPIMDC(G, nt: int, nv: int, nfreq: int, dt: float = 1.0, dr: float = 1.0, tw
     rdtype = {torch.complex64: torch.float32, torch.complex128: torch.float64}.get(cdtype, cdtype)
     nfmax = nfreq
     Gs = G if prescaled else (dr * dt * np.sqrt(nt)) * G
-    Frop = MPIFredholm1(Gs, nv, saveGt=saveGt, usematmul=usematmul, base_comm=base_comm, dtype=_np_of(cdtype))
+    Frop = MPIFredholm1(Gs, nv, saveGt=saveGt, usematmul=usematmul, base_comm=base_comm, dtype=_np_of(cdtype),
+                        scatter_data=(data_domain == "frequency"))
+    Fr0 = Frop            # the MPIFredholm1 itself (slice bookkeeping), also when wrapped by .conj()
     if conj:
         Frop = Frop.conj()
     _, ns, nr = G.shape
@@ -46,9 +57,28 @@ def MPIMDC(G, nt: int, nv: int, nfreq: int, dt: float = 1.0, dr: float = 1.0, tw
                              base_comm=base_comm)
     Iop = MPILinearOperator(Identity(N=nfmax * nr * nv, M=nfft * nr * nv, dtype=_np_of(cdtype)), base_comm=base_comm)
     I1op = MPILinearOperator(Identity(N=nfmax * ns * nv, M=nfft * ns * nv, dtype=_np_of(cdtype)), base_comm=base_comm)
+    if data_domain == "frequency":
+        MDCop = Frop * Iop * Fop
+        MDCop.data_to_frequency = lambda d: mdc_data_to_frequency(d, Fr0, I1op, F1op)
+        MDCop.dtype = np.dtype(_np_of(cdtype))
+        return MDCop
     MDCop = F1op.H * I1op.H * Frop * Iop * Fop
     MDCop.dtype = np.dtype(_np_of(rdtype))   # as the reference: labelled real, carried as complex arrays
     return MDCop
+
+
+def mdc_data_to_frequency(d, Frop, I1op, F1op):
+    """``I1 F1 d`` restricted to this rank's frequency slices: the time-domain (BROADCAST) data of an MDD problem
+    mapped ONCE to the SCATTERed band-limited spectrum the ``data_domain="frequency"`` operator works on"""
+    from ..DistributedArray import DistributedArray, Partition
+    spec = (I1op * F1op).matvec(d)                  # BROADCAST, nfmax * ns * nv
+    per = Frop.nx * Frop.nz
+    rank = Frop.rank
+    out = DistributedArray(global_shape=Frop.shape[0], base_comm=d.base_comm, partition=Partition.SCATTER,
+                           local_shapes=[(int(n) * per,) for n in Frop.nsls], dtype=Frop._tdtype)
+    src = spec.local_array.reshape(-1)[int(Frop.islstart[rank]) * per: int(Frop.islend[rank]) * per]
+    out.local_array.copy_(src)
+    return out
 
 
 def _np_of(t):
