@@ -247,6 +247,12 @@ int b2_peer_vec_create(int rank, int size, void* const* boxes_host, b2_peer_vec*
 int b2_peer_vec_destroy(b2_peer_vec* h);
 int b2_peer_vec_allreduce(b2_peer_vec* h, void* buf_dev, size_t n, int dtype, void* stream);
 
+/* One-shot Allgather(v) over the same mailboxes (every chunk <= b2_peer_vec_max_bytes()): recv = concatenation of the
+ * ranks' counts_host[r] elements.  The latency-regime replacement of the pad-to-max NCCL gather of
+ * utils/_nccl.py:363-403 (e.g. the 128 KB model vector of MPIMatrixMult's single-column apply). */
+int b2_peer_vec_allgatherv(b2_peer_vec* h, const void* send, void* recv, const size_t* counts_host, int dtype,
+                           void* stream);
+
 /* ---- NCCL collectives (utils/_nccl.py:98-403, utils/_mpi.py:21-344,
  *      Distributed.py:35-349) --------------------------------------------- */
 int b2_get_unique_id(void* id128_host);                       /* _nccl.py:98-132 */

@@ -73,6 +73,13 @@ def allgatherv(comm: Comm, send: torch.Tensor, counts: Sequence[int],
         return out
     _flat(send)
     arr = (C.c_size_t * comm.size)(*[int(c) for c in counts])
+    if max(int(c) for c in counts) * send.element_size() <= _PEER_VEC_MAX:
+        # latency regime: one-shot all-gather over peer memory (rank-invariant choice: counts and dtype only)
+        pv = comm.peer_vec
+        if pv is not None:
+            _lib.check(_lib.lib.b2_peer_vec_allgatherv(pv, send.data_ptr() if send.numel() else None, out.data_ptr(), arr,
+                                                       _lib.code(send.dtype), _lib.stream()), "b2_peer_vec_allgatherv")
+            return out
     _lib.check(_lib.lib.b2_allgatherv(comm.nccl, send.data_ptr(), out.data_ptr(), arr,
                                       _lib.code(send.dtype), _lib.stream()), "b2_allgatherv")
     return out

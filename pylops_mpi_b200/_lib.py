@@ -115,6 +115,7 @@ def _load():
         "b2_peer_vec_create": ([i, i, C.POINTER(vp), C.POINTER(vp)], i),
         "b2_peer_vec_destroy": ([vp], i),
         "b2_peer_vec_allreduce": ([vp, vp, sz, i, vp], i),
+        "b2_peer_vec_allgatherv": ([vp, vp, vp, C.POINTER(sz), i, vp], i),
         "b2_get_unique_id": ([vp], i),
         "b2_comm_create": ([i, i, vp, i, C.POINTER(vp)], i),
         "b2_comm_split": ([vp, i, i, C.POINTER(vp)], i),

@@ -177,6 +177,60 @@ peer_allreduce_vec_kernel(VecPtrs pp, int rank, int P, T* __restrict__ buf, size
 }
 }  // namespace
 
+// One-shot ALL-GATHER(v) over the same mailboxes: every rank pushes its chunk into its slot of every peer's
+// mailbox, publishes its flag, waits for the P flags in its own mailbox and copies the P slots into the contiguous
+// result (rank order).  Replaces ncclAllGather in the latency regime (<= 256 KB per rank): the gather of the model
+// vector in MPIMatrixMult's M = 1 "32768-vec" apply, small BROADCAST rebuilds (Fredholm1 KATs) ...
+struct GatherCounts {
+  unsigned long long bytes[PEER_MAX];   // chunk size of every rank
+  unsigned long long off[PEER_MAX];     // byte offset of every rank's chunk in the result
+};
+template <typename W>   // W = uint4 / uint32_t / uint16_t copy word
+__global__ void __launch_bounds__(256)
+peer_allgather_vec_kernel(VecPtrs pp, int rank, int P, const char* __restrict__ send, char* __restrict__ recv,
+                          GatherCounts gc, unsigned long long* seq_dev) {
+  const unsigned long long seq = *reinterpret_cast<volatile unsigned long long*>(seq_dev) + 1ull;
+  const int par = (int)(seq & 1ull);
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+  const size_t nw = gc.bytes[rank] / sizeof(W);
+  for (int d = 0; d < P; ++d) {
+    W* dst = reinterpret_cast<W*>(vec_slot(pp.p[d], par, rank));
+    for (size_t i = tid; i < nw; i += nthr) dst[i] = reinterpret_cast<const W*>(send)[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  VecBox* me = reinterpret_cast<VecBox*>(pp.p[rank]);
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&me->arrive[par], 1u);
+    if (t == gridDim.x - 1) {
+      me->arrive[par] = 0u;
+      *reinterpret_cast<volatile unsigned long long*>(seq_dev) = seq;
+      __threadfence_system();
+      for (int d = 0; d < P; ++d)
+        st_release_sys(&reinterpret_cast<VecBox*>(pp.p[d])->flag[par][rank], seq);
+    }
+  }
+  if (threadIdx.x < P) {
+    while (ld_acquire_sys(&me->flag[par][threadIdx.x]) < seq) { }
+  }
+  __syncthreads();
+  for (int r = 0; r < P; ++r) {
+    const volatile W* src = reinterpret_cast<const volatile W*>(vec_slot(pp.p[rank], par, r));
+    W* out = reinterpret_cast<W*>(recv + gc.off[r]);
+    const size_t n = gc.bytes[r] / sizeof(W);
+    if constexpr (sizeof(W) == 16) {
+      for (size_t i = tid; i < n; i += nthr) {
+        uint4 v;
+        const volatile uint32_t* s32 = reinterpret_cast<const volatile uint32_t*>(src + i);
+        v.x = s32[0]; v.y = s32[1]; v.z = s32[2]; v.w = s32[3];
+        reinterpret_cast<uint4*>(out)[i] = v;
+      }
+    } else {
+      for (size_t i = tid; i < n; i += nthr) out[i] = src[i];
+    }
+  }
+}
+
 struct b2_peer_vec {
   int rank, size;
   VecPtrs pp;
@@ -222,6 +276,43 @@ extern "C" int b2_peer_vec_allreduce(b2_peer_vec* h, void* buf_dev, size_t n, in
     peer_allreduce_vec_kernel<float><<<grid, 256, 0, st>>>(h->pp, h->rank, h->size, (float*)buf_dev, n, h->seq_dev);
   else
     peer_allreduce_vec_kernel<double><<<grid, 256, 0, st>>>(h->pp, h->rank, h->size, (double*)buf_dev, n, h->seq_dev);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}
+
+
+// recv = concatenation of every rank's counts_host[r] elements (rank order); every chunk <= b2_peer_vec_max_bytes()
+extern "C" int b2_peer_vec_allgatherv(b2_peer_vec* h, const void* send, void* recv, const size_t* counts_host, int dtype,
+                                      void* stream) {
+  if (!h || !recv || !counts_host) return B2_ERR_ARG;
+  const size_t esz = b2_dtype_size(dtype);
+  if (esz == 0) return B2_ERR_DTYPE;
+  GatherCounts gc;
+  size_t off = 0, maxb = 0;
+  int align = 16;
+  for (int r = 0; r < PEER_MAX; ++r) {
+    const size_t b = r < h->size ? counts_host[r] * esz : 0;
+    gc.bytes[r] = b;
+    gc.off[r] = off;
+    if (b > maxb) maxb = b;
+    if (b % 16 || off % 16) align = (b % 4 || off % 4) ? ((align > 2) ? 2 : align) : ((align > 4) ? 4 : align);
+    off += b;
+  }
+  if (maxb > VEC_SLOT_BYTES) return B2_ERR_ARG;
+  if (off == 0) return B2_OK;
+  if (gc.bytes[h->rank] && !send) return B2_ERR_ARG;
+  if (align == 16 && ((send && !b2_aligned16(send)) || !b2_aligned16(recv))) align = 4;
+  if (align == 4 && ((((uintptr_t)send) | ((uintptr_t)recv)) & 3u)) align = 2;
+  if (align == 2 && (esz % 2)) return B2_ERR_ALIGN;
+  size_t work = (maxb + 16 * 256 - 1) / (16 * 256);
+  const unsigned grid = (unsigned)(work < 1 ? 1 : (work > 16 ? 16 : work));    // all CTAs spin on flags: keep them co-resident
+  cudaStream_t st = (cudaStream_t)stream;
+  if (align == 16)
+    peer_allgather_vec_kernel<uint4><<<grid, 256, 0, st>>>(h->pp, h->rank, h->size, (const char*)send, (char*)recv, gc, h->seq_dev);
+  else if (align == 4)
+    peer_allgather_vec_kernel<uint32_t><<<grid, 256, 0, st>>>(h->pp, h->rank, h->size, (const char*)send, (char*)recv, gc, h->seq_dev);
+  else
+    peer_allgather_vec_kernel<uint16_t><<<grid, 256, 0, st>>>(h->pp, h->rank, h->size, (const char*)send, (char*)recv, gc, h->seq_dev);
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
