@@ -14,6 +14,8 @@ from enum import Enum
 from numbers import Integral
 from typing import List, Optional, Sequence, Tuple, Union
 
+import math
+
 import numpy as np
 import torch
 
@@ -679,11 +681,11 @@ class DistributedArray(DistributedMixIn):
         """Move this flat SCATTER vector to the 1-D partition ``dst_sizes``; returns the
         new flat local buffer.  No-op (a view) when the partitions already agree --
         the common case for row-aligned shapes."""
-        src_sizes = [int(np.prod(s)) for s in self._local_shapes]
-        dst_sizes = [int(d) for d in dst_sizes]
+        src_sizes = [math.prod(s) for s in self._local_shapes]
         flat = self._cont().reshape(-1)
         if src_sizes == dst_sizes:
             return flat
+        dst_sizes = [int(d) for d in dst_sizes]
         sends, recvs = repartition_plan(src_sizes, dst_sizes, self.rank)
         out = torch.empty(dst_sizes[self.rank], dtype=self._tdtype, device=flat.device)
         with group(self._base_comm):

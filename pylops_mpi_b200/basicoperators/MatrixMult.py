@@ -310,7 +310,7 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
         if comm.Get_size() > 8:
             raise NotImplementedError("stationary=True maps at most 8 peers")
         self._kA = self._w * self._pa
-        if self._bm % 32 or self._kA % 8 or self._bn % 8:
+        if self._bm % 32 or self._w % 8 or self._bn % 8:
             raise NotImplementedError("stationary=True needs M/Pc % 32 == 0 and 8-aligned tile extents")
         if comm.Get_size() > 1 and comm.peer is None:
             raise NotImplementedError("stationary=True needs CUDA IPC peer access between the ranks")

@@ -5,6 +5,7 @@ grouped NCCL exchange otherwise -- call the body on a ``dims``-shaped array,
 ravel the result."""
 from __future__ import annotations
 
+import math
 import os
 from functools import wraps
 from typing import Callable, Optional
@@ -52,11 +53,16 @@ def reshaped(func: Optional[Callable] = None, forward: Optional[bool] = None,
                 local_shapes = getattr(self, "local_shapes_n")
                 global_shape = x.global_shape
             else:
-                dims = tuple(getattr(self, "dims"))
-                global_shape = dims
-                ext = local_split_sizes(dims[0], x.size)
-                local_shapes = [(e,) + dims[1:] for e in ext]
-            dst = [int(np.prod(s)) for s in local_shapes]
+                # pure integer bookkeeping: once per (operator, world size), not per apply
+                cache = self.__dict__.setdefault("_reshaped_cache", {})
+                hit = cache.get(x.size)
+                if hit is None:
+                    dims = tuple(getattr(self, "dims"))
+                    ext = local_split_sizes(dims[0], x.size)
+                    shapes = [(e,) + dims[1:] for e in ext]
+                    hit = cache[x.size] = (dims, shapes, [int(np.prod(s)) for s in shapes])
+                global_shape, local_shapes = hit[0], hit[1]
+            dst = hit[2] if not stacking else [math.prod(s) for s in local_shapes]
             if STRICT_PARITY and x.size > 1:
                 _strict_check(x, dst)
             buf = x._repartition_flat(dst).view(local_shapes[x.rank])

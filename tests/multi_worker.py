@@ -331,6 +331,40 @@ for solver, fn in (("ista", pm.ista), ("fista", pm.fista)):
         check(f"{solver} {kind} x", host(xs.asarray()), xo, 1e-9, 1e-9)
         check(f"{solver} {kind} cost", cs, co, 1e-9, 0)
 
+# ---- round 2: the driver-visible parity set of bench.py (peer-memory halo, stationary-A / replicated / SUMMA bf16 on
+#      every grid of P, tensor-core Fredholm incl. fused peer all-gather, CGLS graph replay) at this world size ------
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import parity_checks  # noqa: E402
+res = parity_checks.run_all(pm, comm, full_size=(os.environ.get("B2_PARITY_FULL", "0") == "1"))
+assert res["failed"] == 0, res["failures"]
+
+# frequency-domain MDC (scattered spectrum) at P ranks: F1^H I1^H of its gathered output == time-domain MDC
+import warnings  # noqa: E402
+nt, ns, nr, nv = 32, 5, 6, 3
+nfmax = 4 * P
+gt = comm.bcast(np.random.default_rng(31).standard_normal((nt, ns, nr)), 0)
+Gf = np.fft.rfft(gt, n=nt, axis=0)[:nfmax].astype(np.complex128)
+off = np.arange(P + 1) * 4
+mt = comm.bcast(np.random.default_rng(32).standard_normal(nt * nr * nv), 0)
+md = pm.DistributedArray.to_dist(mt, partition=pm.Partition.BROADCAST)
+Mt = pm.MPIMDC(Gf[off[rank]:off[rank + 1]], nt=nt, nv=nv, nfreq=nfmax, dt=0.004, dr=2.0, twosided=False)
+Mf = pm.MPIMDC(Gf[off[rank]:off[rank + 1]], nt=nt, nv=nv, nfreq=nfmax, dt=0.004, dr=2.0, twosided=False, data_domain="frequency")
+G_loc = [Gf[off[r]:off[r + 1]] for r in range(P)]
+dt_ = Mt @ md
+check("mdc time", host(dt_.asarray()).real, o.mdc(G_loc, mt, nt, nv, False, False, dt=0.004, dr=2.0), 1e-10, 1e-10)
+df = Mf @ md
+assert df.partition is pm.Partition.SCATTER
+spec = host(Mf.data_to_frequency(dt_).asarray())
+got = host(df.asarray())
+check("mdc frequency (non-DC bins)", got[ns * nv:], spec[ns * nv:], 1e-9, 1e-9 * np.abs(spec).max())
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    x0 = pm.DistributedArray.to_dist(np.zeros(nt * nr * nv), partition=pm.Partition.BROADCAST)
+    xt_, *_ = pm.cgls(Mt, dt_, x0=x0, niter=6, tol=0.0)
+    xf_, *_ = pm.cgls(Mf, Mf.data_to_frequency(dt_), x0=x0, niter=6, tol=0.0)
+check("mdd iterates time vs frequency domain", host(xf_.asarray()).real, host(xt_.asarray()).real, 1e-6,
+      1e-6 * np.abs(host(xt_.asarray())).max())
+
 comm.Barrier()
 torch.cuda.synchronize()
 print(f"MULTI_WORKER_OK rank={rank} size={P}")
