@@ -223,6 +223,8 @@ int b2_fredholm_plan_create(b2_ctx* ctx, const void* G, size_t nsl, size_t nx, s
 int b2_fredholm_plan_destroy(b2_fredholm_plan* plan);
 int b2_fredholm_apply(b2_fredholm_plan* plan, const void* x, void* y, void* const* peers_host, int npeers,
                       int adjoint, void* stream);
+/* profiling aid: parts = 1 packs x only, 2 = product on the planes of the previous pack, 3 = both */
+int b2_fredholm_apply_parts(b2_fredholm_plan* plan, const void* x, void* y, int adjoint, int parts, void* stream);
 /* peer-mappable device buffers (cudaMalloc) and CUDA IPC handle plumbing (64-byte handles) */
 int b2_symm_alloc(size_t bytes, void** out);
 int b2_symm_free(void* p);

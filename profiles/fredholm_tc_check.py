@@ -80,7 +80,13 @@ def main():
         def simt():
             L.lib.b2_batched_gemm(L.ctx(), G.data_ptr(), x.data_ptr(), y.data_ptr(), nsl, nx, ny, nz, 0, L.C64, st)
 
-        for name, fn in (("tc_pack+product", tc), ("simt", simt)):
+        def tc_pack():
+            L.lib.b2_fredholm_apply_parts(h, x.data_ptr(), y.data_ptr(), 0, 1, st)
+
+        def tc_product():
+            L.lib.b2_fredholm_apply_parts(h, x.data_ptr(), y.data_ptr(), 0, 2, st)
+
+        for name, fn in (("tc_pack+product", tc), ("tc_pack_only", tc_pack), ("tc_product_only", tc_product), ("simt", simt)):
             for _ in range(10):
                 fn()
             torch.cuda.synchronize()

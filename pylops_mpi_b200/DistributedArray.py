@@ -388,14 +388,25 @@ class DistributedArray(DistributedMixIn):
         a, b = self._pair(x)
         return self._mine_from(self._lincomb(1.0, a, -1.0, b))
 
+    def _iupdate(self, other: "DistributedArray", sign: float):
+        """self <- self + sign * other.  Same dtype: one in-place kernel.  Mixed dtypes: the reference evaluates
+        ``self[:] = self.local_array + other.local_array`` (DistributedArray.py:619-624): the sum in the promoted
+        dtype, then a NumPy __setitem__ cast into self -- reproduced exactly (sum first, cast second)"""
+        if other._tdtype == self._tdtype:
+            a = self._cont()
+            self._lincomb(1.0, a, sign, other._cont(), out=a)
+            if a is not self._local_array:
+                self._local_array.copy_(a)
+            return self
+        xa, xb = self._pair(other)
+        res = self._mine_from(self._lincomb(1.0, xa, sign, xb))
+        self._local_array.copy_(res._local_array)
+        return self
+
     def __isub__(self, x):
         self._check_partition_shape(x)
         self._check_mask(x)
-        a = self._cont()
-        self._lincomb(1.0, a, -1.0, self._as_mine(x), out=a)
-        if a is not self._local_array:
-            self._local_array.copy_(a)
-        return self
+        return self._iupdate(x, -1.0)
 
     def __mul__(self, x):
         return self.multiply(x)
@@ -412,11 +423,7 @@ class DistributedArray(DistributedMixIn):
     def iadd(self, dist_array):
         self._check_partition_shape(dist_array)
         self._check_mask(dist_array)
-        a = self._cont()
-        self._lincomb(1.0, a, 1.0, self._as_mine(dist_array), out=a)
-        if a is not self._local_array:
-            self._local_array.copy_(a)
-        return self
+        return self._iupdate(dist_array, 1.0)
 
     def multiply(self, dist_array):
         if isinstance(dist_array, DistributedArray):

@@ -83,7 +83,7 @@ template <int MODE, uint32_t BK>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fredholm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    float* __restrict__ Y, const PeerOut peers, const float* __restrict__ invA,
-                   const float* __restrict__ invB, uint32_t nstrips, uint32_t strip_cols, uint32_t nsl, uint32_t m,
+                   const float* __restrict__ invB, uint32_t nz, uint32_t zdiv, uint32_t nsl, uint32_t m,
                    uint32_t n, uint32_t kpad, uint32_t n_umma, int vec_ok) {
   using C = Cfg<MODE, BK>;
   constexpr uint32_t NPL = C::NPL;
@@ -195,7 +195,7 @@ fredholm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tcgen05_fence_after();
       const uint32_t row = m_blk * BM + g * 32 + lane;
       const size_t roff = ((size_t)s * m + row) * n;
-      const float sa_inv = MODE == MODE_H2 ? invA[s] : 1.f;
+      const float sa_inv = (MODE == MODE_H2 && row < m) ? invA[(size_t)s * m + row] : 1.f;   // per output row
 #pragma unroll 1
       for (uint32_t c0 = 0; c0 < n_umma; c0 += 32) {
         uint32_t v[32], w[32];
@@ -204,12 +204,14 @@ fredholm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tmem_ld_wait();
         const uint32_t col0 = n_blk * BN + c0;
         if (MODE == MODE_H2) {
-          // undo the power-of-two operand scales (exact) and the 2^11 of the correction terms
-          const uint32_t strip = col0 / strip_cols;
-          const float sc = sa_inv * (strip < nstrips ? invB[(size_t)s * nstrips + strip] : 0.f);
+          // undo the power-of-two operand scales (exact: per output row of op(G), per column of x) and the 2^11
+          // of the correction terms
 #pragma unroll
-          for (uint32_t j = 0; j < 32; ++j)
+          for (uint32_t j = 0; j < 32; ++j) {
+            const uint32_t z = (col0 + j) / zdiv;
+            const float sc = sa_inv * (z < nz ? __ldg(&invB[(size_t)s * nz + z]) : 0.f);
             v[j] = __float_as_uint(fmaf(__uint_as_float(w[j]), 1.f / 2048.f, __uint_as_float(v[j])) * sc);
+          }
         } else {
 #pragma unroll
           for (uint32_t j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
@@ -296,12 +298,21 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return r;
 }
 
-// h2 only: scale of each G slice (operator state, once per plan)
-__global__ void __launch_bounds__(256) slice_scale_kernel(const float* __restrict__ G, size_t per_slice, float* scA, float* invA) {
-  __shared__ float red[8];
-  const float* g = G + (size_t)blockIdx.x * per_slice;
+// h2 only: power-of-two scale of every output ROW of op(G[s]) (operator state, once per plan and direction):
+//   dir 0: row i of G[s] (contiguous);  dir 1: row j of G[s]^H = column j of G[s]
+__global__ void __launch_bounds__(128) row_scale_kernel(const float* __restrict__ G, size_t nx, size_t ny, int cx, int dir,
+                                                         float* scA, float* invA) {
+  __shared__ float red[4];
+  const size_t rows = dir == 0 ? nx : ny, inner = dir == 0 ? ny : nx;
+  const size_t s = blockIdx.x / rows, r = blockIdx.x % rows;
+  const size_t mul = cx ? 2 : 1;
+  const float* g = G + s * nx * ny * mul;
   float am = 0.f;
-  for (size_t i = threadIdx.x; i < per_slice; i += blockDim.x) am = fmaxf(am, fabsf(g[i]));
+  for (size_t q = threadIdx.x; q < inner * mul; q += blockDim.x) {
+    const size_t e = q / mul, c = q % mul;
+    const size_t idx = dir == 0 ? (r * ny + e) : (e * ny + r);
+    am = fmaxf(am, fabsf(g[idx * mul + c]));
+  }
   am = block_max(am, red);
   if (threadIdx.x == 0) pow2_scale(am, &scA[blockIdx.x], &invA[blockIdx.x]);
 }
@@ -326,7 +337,7 @@ __global__ void pack_g_kernel(const float* __restrict__ G, unsigned short* __res
       v = cx ? G[2 * idx + cc] : G[idx];
       if (dir == 1 && cc == 1) v = -v;
     }
-    const Split<MODE> sp = split<MODE>(v, MODE == MODE_H2 ? scA[s] : 1.f);
+    const Split<MODE> sp = split<MODE>(v, MODE == MODE_H2 ? scA[s * rows + r] : 1.f);
     const size_t base = ((s * NPL) * rows + r) * kpad + c;
 #pragma unroll
     for (uint32_t p = 0; p < NPL; ++p) out[base + (size_t)p * rows * kpad] = sp.p[p];
@@ -336,26 +347,27 @@ __global__ void pack_g_kernel(const float* __restrict__ G, unsigned short* __res
 // per apply: planes of X'^T,  BT[s][p][n'][k'] (k' < kpad; columns in [kp, kpad) are written as zeros)
 //   complex: n' = 2z+d, k' = 2k+c:  (c,d) = (0,0) re, (1,0) -im, (0,1) im, (1,1) re
 //   real   : n' = z,    k' = k
-// One block per (32-column strip of x, slice): h2 first takes the strip's amax (power-of-two scale, its inverse
-// goes to invB for the epilogue), then 32 x 32 tiles are transposed through shared memory and written as
-// 16-byte (complex) / 8-byte (real) vectors along k'.
+// One 1024-thread block per (32-column strip of x, slice): h2 first takes every COLUMN's amax over k (power-of-two
+// scale per column, its inverse goes to invB for the epilogue), then 128 x 32 tiles are transposed through shared
+// memory and written as 16-byte (complex) / 8-byte (real) vectors along k'.
+constexpr uint32_t PK_THREADS = 1024, PK_ROWS = 128;
 template <bool CX, int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PK_THREADS)
 pack_x_kernel(const float* __restrict__ x, unsigned short* __restrict__ BT, float* __restrict__ invB, uint32_t K,
               uint32_t nz, uint32_t nrows, uint32_t kpad) {
   constexpr uint32_t NPL = npl_of(MODE);
-  __shared__ float2 tile[32][33];
-  __shared__ float red[8];
+  __shared__ float2 tile[PK_ROWS][33];
+  __shared__ float colmax[32][33];
+  __shared__ float scale_s[32];
   grid_dep_launch();               // PDL: the product kernel may start its prologue / A loads now
   const uint32_t s = blockIdx.y, z0 = blockIdx.x * ZSTRIP;
   const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const float* xs = x + (size_t)s * K * nz * (CX ? 2 : 1);
-  float scale = 1.f;
   if (MODE == MODE_H2) {
     float am = 0.f;
     const uint32_t z = z0 + tx;
     if (z < nz)
-      for (uint32_t k = ty; k < K; k += 8) {
+      for (uint32_t k = ty; k < K; k += 32) {
         if (CX) {
           const float2 v = reinterpret_cast<const float2*>(xs)[(size_t)k * nz + z];
           am = fmaxf(am, fmaxf(fabsf(v.x), fabsf(v.y)));
@@ -363,17 +375,25 @@ pack_x_kernel(const float* __restrict__ x, unsigned short* __restrict__ BT, floa
           am = fmaxf(am, fabsf(xs[(size_t)k * nz + z]));
         }
       }
-    am = block_max(am, red);
-    float inv;
-    pow2_scale(am, &scale, &inv);
-    if (threadIdx.x == 0) invB[(size_t)s * gridDim.x + blockIdx.x] = inv;
+    colmax[ty][tx] = am;
+    __syncthreads();
+    if (ty == 0) {
+      float m = colmax[0][tx];
+      for (int i = 1; i < 32; ++i) m = fmaxf(m, colmax[i][tx]);
+      float sc, inv;
+      pow2_scale(m, &sc, &inv);
+      scale_s[tx] = sc;
+      if (z < nz) invB[(size_t)s * nz + z] = inv;
+    }
+    __syncthreads();
   }
   const size_t plane = (size_t)nrows * kpad;
   unsigned short* base = BT + (size_t)s * NPL * plane;
-  const uint32_t zz = threadIdx.x >> 3, kq = threadIdx.x & 7;     // write phase: one z, four consecutive k
-  const uint32_t kspan = (kpad / (CX ? 2 : 1) + 31) / 32 * 32;    // cover the padding columns too
-  for (uint32_t k0 = 0; k0 < kspan; k0 += 32) {
-    for (uint32_t kk = ty; kk < 32; kk += 8) {
+  const uint32_t zz = threadIdx.x >> 5, kq = threadIdx.x & 31;     // write phase: one z, four consecutive k
+  const float scale = MODE == MODE_H2 ? scale_s[zz] : 1.f;
+  const uint32_t kcover = kpad / (CX ? 2 : 1);                     // k values whose k' columns exist (incl. padding)
+  for (uint32_t k0 = 0; k0 < kcover; k0 += PK_ROWS) {
+    for (uint32_t kk = ty; kk < PK_ROWS; kk += 32) {
       const uint32_t k = k0 + kk, z = z0 + tx;
       float2 v = make_float2(0.f, 0.f);
       if (k < K && z < nz) {
@@ -444,7 +464,8 @@ struct b2_fredholm_plan {
   size_t m[2], kp[2], kpad[2];
   unsigned short* A[2];         // planes of op(G): [nsl][npl][m][kpad]
   unsigned short* BT[2];        // planes of X'^T : [nsl][npl][n][kpad]   (per-apply workspace)
-  float *scA, *invA, *invB;     // h2: per-slice scale of G (and inverse), inverse scale per (slice, x strip)
+  float *scA[2], *invA[2], *invB;   // h2: power-of-two scale per (slice, output row) of op(G) and its inverse (per
+                                    // direction), inverse scale per (slice, column of x)
   uint32_t n, n_umma, nstrips;  // output columns (real), UMMA N, 32-column strips of x
   CUtensorMap tmA[2], tmB[2];
 };
@@ -455,8 +476,10 @@ extern "C" int b2_fredholm_plan_destroy(b2_fredholm_plan* pl) {
     if (pl->A[d]) cudaFree(pl->A[d]);
     if (pl->BT[d]) cudaFree(pl->BT[d]);
   }
-  if (pl->scA) cudaFree(pl->scA);
-  if (pl->invA) cudaFree(pl->invA);
+  for (int d = 0; d < 2; ++d) {
+    if (pl->scA[d]) cudaFree(pl->scA[d]);
+    if (pl->invA[d]) cudaFree(pl->invA[d]);
+  }
   if (pl->invB) cudaFree(pl->invB);
   delete pl;
   return B2_OK;
@@ -489,16 +512,18 @@ extern "C" int b2_fredholm_plan_create(b2_ctx* ctx, const void* G, size_t nsl, s
   pl->m[0] = nx; pl->kp[0] = ny * mul;
   pl->m[1] = ny; pl->kp[1] = nx * mul;
   int rc = B2_OK;
-  cudaError_t e = cudaMalloc((void**)&pl->scA, nsl * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&pl->invA, nsl * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc((void**)&pl->invB, nsl * pl->nstrips * sizeof(float));
+  cudaError_t e = cudaMalloc((void**)&pl->invB, nsl * nz * sizeof(float));
   if (e != cudaSuccess) rc = (int)e;
-  if (rc == B2_OK && pl->mode == MODE_H2) {
-    slice_scale_kernel<<<(unsigned)nsl, 256>>>((const float*)G, nx * ny * mul, pl->scA, pl->invA);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) rc = (int)e;
-  }
   for (int d = 0; d < 2 && rc == B2_OK; ++d) {
+    e = cudaMalloc((void**)&pl->scA[d], nsl * pl->m[d] * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pl->invA[d], nsl * pl->m[d] * sizeof(float));
+    if (e != cudaSuccess) { rc = (int)e; break; }
+    if (pl->mode == MODE_H2) {
+      if (nsl * pl->m[d] > 0x7fffffffull) { rc = B2_ERR_ARG; break; }
+      row_scale_kernel<<<(unsigned)(nsl * pl->m[d]), 128>>>((const float*)G, nx, ny, pl->cx, d, pl->scA[d], pl->invA[d]);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) { rc = (int)e; break; }
+    }
     pl->kpad[d] = round_up(pl->kp[d], 8);
     const size_t a_elems = nsl * npl * pl->m[d] * pl->kpad[d], b_elems = nsl * npl * (size_t)pl->n * pl->kpad[d];
     e = cudaMalloc((void**)&pl->A[d], a_elems * 2);
@@ -509,9 +534,9 @@ extern "C" int b2_fredholm_plan_create(b2_ctx* ctx, const void* G, size_t nsl, s
     size_t blocks = (total + 255) / 256;
     if (blocks > (size_t)ctx->sm_count * 32) blocks = (size_t)ctx->sm_count * 32;
     if (pl->mode == MODE_B3)
-      pack_g_kernel<MODE_B3><<<(unsigned)blocks, 256>>>((const float*)G, pl->A[d], pl->scA, nsl, nx, ny, pl->cx, d, pl->m[d], pl->kpad[d]);
+      pack_g_kernel<MODE_B3><<<(unsigned)blocks, 256>>>((const float*)G, pl->A[d], pl->scA[d], nsl, nx, ny, pl->cx, d, pl->m[d], pl->kpad[d]);
     else
-      pack_g_kernel<MODE_H2><<<(unsigned)blocks, 256>>>((const float*)G, pl->A[d], pl->scA, nsl, nx, ny, pl->cx, d, pl->m[d], pl->kpad[d]);
+      pack_g_kernel<MODE_H2><<<(unsigned)blocks, 256>>>((const float*)G, pl->A[d], pl->scA[d], nsl, nx, ny, pl->cx, d, pl->m[d], pl->kpad[d]);
     e = cudaGetLastError();
     if (e != cudaSuccess) { rc = (int)e; break; }
     const bool fp16 = pl->mode == MODE_H2;
@@ -557,9 +582,8 @@ static int launch_product(b2_fredholm_plan* pl, int d, float* y, const PeerOut& 
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  const uint32_t strip_cols = ZSTRIP * (pl->cx ? 2u : 1u);
-  B2_CUDA(cudaLaunchKernelEx(&cfg, fredholm_tc_kernel<MODE, BK>, pl->tmA[d], pl->tmB[d], y, po, (const float*)pl->invA,
-                             (const float*)pl->invB, pl->nstrips, strip_cols, (uint32_t)pl->nsl, m, pl->n,
+  B2_CUDA(cudaLaunchKernelEx(&cfg, fredholm_tc_kernel<MODE, BK>, pl->tmA[d], pl->tmB[d], y, po, (const float*)pl->invA[d],
+                             (const float*)pl->invB, (uint32_t)pl->nz, pl->cx ? 2u : 1u, (uint32_t)pl->nsl, m, pl->n,
                              (uint32_t)pl->kpad[d], pl->n_umma, vec_ok));
   return B2_OK;
 }
@@ -567,8 +591,8 @@ static int launch_product(b2_fredholm_plan* pl, int d, float* y, const PeerOut& 
 // y[s] = op(G[s]) x[s] for all slices of the plan; peers_host (npeers <= 8, may be NULL/0): the same logical
 // output position in peer GPUs' IPC-mapped buffers -- the epilogue stores every element there too (fused all-gather).
 // Applies of one plan must be stream-ordered (they share the X' workspace).
-extern "C" int b2_fredholm_apply(b2_fredholm_plan* pl, const void* x, void* y, void* const* peers_host, int npeers,
-                                 int adjoint, void* stream) {
+static int fredholm_apply_impl(b2_fredholm_plan* pl, const void* x, void* y, void* const* peers_host, int npeers,
+                               int adjoint, int parts, void* stream) {
   if (!pl || !x || !y || npeers < 0 || npeers > 8 || (npeers && !peers_host)) return B2_ERR_ARG;
   const int d = adjoint ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
@@ -576,18 +600,32 @@ extern "C" int b2_fredholm_apply(b2_fredholm_plan* pl, const void* x, void* y, v
   dim3 grid(pl->nstrips, (unsigned)pl->nsl);
   const float* xf = (const float*)x;
   const uint32_t nz = (uint32_t)pl->nz, kpad = (uint32_t)pl->kpad[d];
-  if (pl->mode == MODE_B3) {
-    if (pl->cx) pack_x_kernel<true, MODE_B3><<<grid, 256, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
-    else pack_x_kernel<false, MODE_B3><<<grid, 256, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
-  } else {
-    if (pl->cx) pack_x_kernel<true, MODE_H2><<<grid, 256, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
-    else pack_x_kernel<false, MODE_H2><<<grid, 256, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
+  if (parts & 1) {
+    if (pl->mode == MODE_B3) {
+      if (pl->cx) pack_x_kernel<true, MODE_B3><<<grid, PK_THREADS, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
+      else pack_x_kernel<false, MODE_B3><<<grid, PK_THREADS, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
+    } else {
+      if (pl->cx) pack_x_kernel<true, MODE_H2><<<grid, PK_THREADS, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
+      else pack_x_kernel<false, MODE_H2><<<grid, PK_THREADS, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
+    }
+    B2_LAUNCH_CHECK();
   }
-  B2_LAUNCH_CHECK();
+  if (!(parts & 2)) return B2_OK;
   PeerOut po;
   po.n = npeers;
   for (int i = 0; i < 8; ++i) po.p[i] = i < npeers ? (float*)peers_host[i] : nullptr;
   if (pl->mode == MODE_B3)
     return pl->bk == 64 ? launch_product<MODE_B3, 64>(pl, d, (float*)y, po, st) : launch_product<MODE_B3, 32>(pl, d, (float*)y, po, st);
   return pl->bk == 64 ? launch_product<MODE_H2, 64>(pl, d, (float*)y, po, st) : launch_product<MODE_H2, 32>(pl, d, (float*)y, po, st);
+}
+
+extern "C" int b2_fredholm_apply(b2_fredholm_plan* pl, const void* x, void* y, void* const* peers_host, int npeers,
+                                 int adjoint, void* stream) {
+  return fredholm_apply_impl(pl, x, y, peers_host, npeers, adjoint, 3, stream);
+}
+
+// profiling aid: parts = 1 packs x only, 2 runs the product on the planes of the previous pack, 3 = both
+extern "C" int b2_fredholm_apply_parts(b2_fredholm_plan* pl, const void* x, void* y, int adjoint, int parts, void* stream) {
+  if (parts < 1 || parts > 3) return B2_ERR_ARG;
+  return fredholm_apply_impl(pl, x, y, nullptr, 0, adjoint, parts, stream);
 }
