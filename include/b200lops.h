@@ -69,6 +69,13 @@ int b2_lincomb(b2_ctx* ctx, void* out, const double a[2], const void* x, const d
 int b2_lincomb_dev(b2_ctx* ctx, void* out, const double* a_dev, double a_scale, const void* x,
                    const double* b_dev, double b_scale, const void* y, size_t n, int dtype,
                    void* stream);
+/* b2_lincomb_dev fused with the reduction the CGLS recurrence needs next: out = a x + b y (real device scalars) and
+ * norm2_dev[0] = sum |out|^2 (float64, local partial; norm2_dev[1] = 0 for complex dtypes so that the caller's
+ * (re, im) slot layout is kept).  x.x after x += a c, s.s after s -= a q, c.c after c = r + b c
+ * (cls_basic.py:389-401): one pass and one launch each instead of two.  Shares the ctx reduction workspace. */
+int b2_lincomb_dev_norm2(b2_ctx* ctx, void* out, const double* a_dev, double a_scale, const void* x,
+                         const double* b_dev, double b_scale, const void* y, size_t n, int dtype,
+                         double* norm2_dev, void* stream);
 /* out = op(x) * y element-wise (DistributedArray.multiply, :630-652) */
 int b2_mul(b2_ctx* ctx, void* out, const void* x, const void* y, size_t n, int dtype,
            int conj_x, void* stream);

@@ -71,6 +71,7 @@ def _load():
         "b2_ctx_sm_count": ([vp, C.POINTER(i)], i),
         "b2_lincomb": ([vp, vp, dp, vp, dp, vp, sz, i, i, vp], i),
         "b2_lincomb_dev": ([vp, vp, vp, d, vp, vp, d, vp, sz, i, vp], i),
+        "b2_lincomb_dev_norm2": ([vp, vp, vp, d, vp, vp, d, vp, sz, i, vp, vp], i),
         "b2_mul": ([vp, vp, vp, vp, sz, i, i, vp], i),
         "b2_fill": ([vp, vp, dp, sz, i, vp], i),
         "b2_dot": ([vp, vp, vp, sz, i, i, vp, vp], i),

@@ -552,3 +552,109 @@ extern "C" int b2_norm_axis(b2_ctx* ctx, const void* x, size_t n_outer, size_t n
   B2_LAUNCH_CHECK();
   return B2_OK;
 }
+
+
+// ---- fused solver update + norm: out = (a_scale * *a_dev) x + (b_scale * *b_dev) y  and  norm2 = sum |out|^2 ---------
+// The three vector updates of a CGLS iteration (cls_basic.py:390-391, 396) each feed a reduction the recurrence needs
+// right after (x.x, s.s, c.c): one pass instead of an update pass plus a reduction pass, and three launches fewer
+// per iteration.  Real coefficients (device scalars), so complex arrays are processed as arrays of 2n reals; the
+// squared values are accumulated in float64 from the ROUNDED stored result, i.e. the same number a separate
+// b2_dot_multi pass over `out` would produce.  Deterministic last-CTA fold like reduce_kernel.
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(RED_THREADS)
+axpby_norm2_kernel(T* out, const double* a_dev, double a_scale, const T* x, const double* b_dev, double b_scale,
+                   const T* y, size_t n_real, int vec, double* __restrict__ partials, unsigned int* __restrict__ ticket,
+                   double* __restrict__ res, int zero_second) {
+  constexpr int V = Vec16<T>::N;
+  const T a = (T)(a_scale * (a_dev ? *a_dev : 1.0)), b = (T)(b_scale * (b_dev ? *b_dev : 1.0));
+  double acc = 0.0;
+  const size_t stride = (size_t)gridDim.x * RED_THREADS;
+  size_t i = (size_t)blockIdx.x * RED_THREADS + threadIdx.x;
+  if (vec) {
+    const size_t nvec = n_real / V;
+    for (; i < nvec; i += stride) {
+      const Vec16<T> vx = load_vec_coherent(x + i * V), vy = load_vec_coherent(y + i * V);
+      Vec16<T> o;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        o.v[k] = a * vx.v[k] + b * vy.v[k];
+        acc = fma((double)o.v[k], (double)o.v[k], acc);
+      }
+      store_vec(out + i * V, o);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      for (size_t t = nvec * V; t < n_real; ++t) {
+        const T o = a * x[t] + b * y[t];
+        out[t] = o;
+        acc = fma((double)o, (double)o, acc);
+      }
+  } else {
+    for (; i < n_real; i += stride) {
+      const T o = a * x[i] + b * y[i];
+      out[i] = o;
+      acc = fma((double)o, (double)o, acc);
+    }
+  }
+  __shared__ double smem[RED_THREADS / 32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double v = warp_comb<MODE_SUM>(acc);
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < RED_THREADS / 32 ? smem[lane] : 0.0;
+    v = warp_comb<MODE_SUM>(v);
+    if (lane == 0) partials[blockIdx.x] = v;
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    if (warp == 0) {
+      double w = 0.0;
+      for (unsigned int bb = lane; bb < gridDim.x; bb += 32) w += __ldcg(&partials[bb]);
+      w = warp_comb<MODE_SUM>(w);
+      if (lane == 0) {
+        res[0] = w;
+        if (zero_second) res[1] = 0.0;
+        *ticket = 0u;
+      }
+    }
+  }
+}
+}  // namespace
+
+extern "C" int b2_lincomb_dev_norm2(b2_ctx* ctx, void* out, const double* a_dev, double a_scale, const void* x,
+                                    const double* b_dev, double b_scale, const void* y, size_t n, int dtype,
+                                    double* norm2_dev, void* stream) {
+  if (!ctx || !norm2_dev) return B2_ERR_ARG;
+  const bool cx = (dtype == B2_C64 || dtype == B2_C128);
+  const bool dbl = (dtype == B2_F64 || dtype == B2_C128);
+  if (!cx && dtype != B2_F32 && dtype != B2_F64) return B2_ERR_DTYPE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    zero_out_kernel<<<1, 32, 0, st>>>(norm2_dev, cx ? 2 : 1, 0.0);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+  }
+  if (!out || !x || !y) return B2_ERR_ARG;
+  const size_t n_real = cx ? 2 * n : n;
+  const int V = dbl ? 2 : 4;
+  const int vec = (b2_aligned16(out) && b2_aligned16(x) && b2_aligned16(y) && n_real >= (size_t)V) ? 1 : 0;
+  const int grid = red_grid(ctx, vec ? n_real / V : n_real);
+  if (dbl)
+    axpby_norm2_kernel<double><<<grid, RED_THREADS, 0, st>>>((double*)out, a_dev, a_scale, (const double*)x, b_dev, b_scale,
+                                                            (const double*)y, n_real, vec, ctx->red_partials, ctx->tickets,
+                                                            norm2_dev, cx ? 1 : 0);
+  else
+    axpby_norm2_kernel<float><<<grid, RED_THREADS, 0, st>>>((float*)out, a_dev, a_scale, (const float*)x, b_dev, b_scale,
+                                                           (const float*)y, n_real, vec, ctx->red_partials, ctx->tickets,
+                                                           norm2_dev, cx ? 1 : 0);
+  B2_LAUNCH_CHECK();
+  return B2_OK;
+}

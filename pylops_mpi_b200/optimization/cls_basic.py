@@ -147,6 +147,29 @@ def _lincomb_dev(out: DistributedArray, a_dev: Optional[torch.Tensor], ai: int, 
         out.local_array.copy_(o)
 
 
+def _lincomb_dev_norm2(out: DistributedArray, a_dev: Optional[torch.Tensor], ai: int, a_scale: float,
+                       x: DistributedArray, b_dev: Optional[torch.Tensor], bi: int, b_scale: float,
+                       y: DistributedArray, dev: torch.Tensor, slot: int) -> bool:
+    """out = (a_scale a_dev[ai]) x + (b_scale b_dev[bi]) y AND dev[slot] = sum |out|^2 (local partial) in ONE kernel.
+    Falls back (returns False after doing the plain update) for BROADCAST arrays -- their reduction runs on the
+    re-scattered view -- and mixed dtypes."""
+    from ..DistributedArray import Partition
+    o = out._cont()
+    fusable = out.partition is Partition.SCATTER and o is out.local_array and \
+        x._tdtype == out._tdtype and y._tdtype == out._tdtype and out._tdtype in (torch.float32, torch.float64,
+                                                                                 torch.complex64, torch.complex128)
+    if not fusable:
+        _lincomb_dev(out, a_dev, ai, a_scale, x, b_dev, bi, b_scale, y)
+        return False
+    _lib.check(_lib.lib.b2_lincomb_dev_norm2(_lib.ctx(), o.data_ptr(),
+                                             (a_dev.data_ptr() + 8 * ai) if a_dev is not None else None, float(a_scale),
+                                             x._cont().data_ptr(),
+                                             (b_dev.data_ptr() + 8 * bi) if b_dev is not None else None, float(b_scale),
+                                             y._cont().data_ptr(), o.numel(), _lib.code(o.dtype),
+                                             dev.data_ptr() + 8 * slot, _lib.stream()), "b2_lincomb_dev_norm2")
+    return True
+
+
 class CG(Solver):
     """cls_basic.py:12-249"""
 
@@ -347,20 +370,23 @@ class CGLS(Solver):
         sub = self.c.sub_comm
         self.q = self.Op.matvec(self.c)
         _dots_device([self.q], dev, QQ)
-        _dots_device([self.c], dev, CC)
+        if not self._cc_ready:                      # c.c normally comes fused with the update of c (end of the body)
+            _dots_device([self.c], dev, CC)
         allreduce_(sub, dev[0:2 * st], "sum")
         _scalar_div(dev, A_, dev, KOLD, dev, QQ, dev, CC, self.damp)
-        _lincomb_dev(x, dev, A_, 1.0, self.c, None, 0, 1.0, x)
-        _lincomb_dev(self.s, dev, A_, -1.0, self.q, None, 0, 1.0, self.s)
+        # x += a c (+ x.x), s -= a q (+ s.s): update and the reduction the cost needs, one pass each
+        if not _lincomb_dev_norm2(x, dev, A_, 1.0, self.c, None, 0, 1.0, x, dev, XX):
+            _dots_device([x], dev, XX)
+        if not _lincomb_dev_norm2(self.s, dev, A_, -1.0, self.q, None, 0, 1.0, self.s, dev, SS):
+            _dots_device([self.s], dev, SS)
         r = self.Op.rmatvec(self.s)
         if self.damp != 0.0:
             r.axpy_(-self.damp, x)
         _dots_device([r], dev, K)
-        _dots_device([self.s], dev, SS)
-        _dots_device([x], dev, XX)
         allreduce_(sub, dev[4:4 + 3 * st], "sum")
         _scalar_div(dev, B_, dev, K, dev, KOLD)
-        _lincomb_dev(self.c, None, 0, 1.0, r, dev, B_, 1.0, self.c)
+        # c = r + b c (+ c.c for the next iteration's step length)
+        self._cc_ready = _lincomb_dev_norm2(self.c, None, 0, 1.0, r, dev, B_, 1.0, self.c, dev, CC)
         _lib.check(_lib.lib.b2_history_push(dev.data_ptr() + 8 * K, 3, st, hist.data_ptr(), it_dev.data_ptr(),
                                             hist.shape[0], dev.data_ptr() + 8 * KOLD, dev.data_ptr() + 8 * K,
                                             _lib.stream()), "b2_history_push")
@@ -398,9 +424,12 @@ class CGLS(Solver):
                 dst.local_array.copy_(src)
             self._dev[14] = self._kold_ckpt
             it_dev.fill_(upto_it)
+            if self._cc_ready:                      # the fused c.c partial belongs to the restored c again
+                _dots_device([self.c], self._dev, self._st)
 
         use_graph = os.environ.get("B2_CGLS_GRAPH", "1") != "0" and _graph_safe(self.Op)
         state = {"graph": None, "use": use_graph, "warm": 0}
+        self._cc_ready = False                      # first body computes c.c itself
 
         def one():
             """one iteration: eager for the first two (lazy workspaces, communicators), then captured once and replayed"""
