@@ -495,7 +495,11 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
         return mine
 
     def _tile_sizes(self, rows_blk: int, rows_full: int):
-        sizes = []
+        cache = self.__dict__.setdefault("_tile_sizes_cache", {})
+        hit = cache.get((rows_blk, rows_full))
+        if hit is not None:
+            return hit
+        sizes = cache[(rows_blk, rows_full)] = []
         for r in range(self.size):
             ri, ci = divmod(r, self._Pc)
             sizes.append(self._extent(rows_blk, rows_full, ri, self._Pr) * self._extent(self._bm, self.M, ci, self._Pc))
