@@ -241,3 +241,30 @@ def test_cgls_blockdiag_cost_is_rounding_noise_below_1e_6():
     assert np.max(np.abs(c1[~big] - c0[~big]) / c0[~big]) > 0.1                  # noise part: > 10 % from ONE ulp
     np.testing.assert_allclose(c1, c0, rtol=1e-6, atol=1e-6 * c0[0])             # the bound the parity checks use
     np.testing.assert_allclose(x1.asarray(), x0.asarray(), rtol=1e-6, atol=1e-6 * np.abs(xt).max())
+
+
+@pytest.mark.parametrize("nt", [31, 32, 64])
+def test_mdc_frequency_domain_claim_isometry_of_the_inverse_transform_stage(nt):
+    """Claim behind MPIMDC(data_domain="frequency") (pylops_mpi_b200/waveeqprocessing/MDC.py): the last two stages of
+    the reference chain, F1^H I1^H (MDC.py:55-69: zero-pad the band, inverse real FFT with the sqrt(2) weighting),
+    are an ISOMETRY on band-limited spectra whose DC bin is real (and whose band excludes Nyquist) -- so CGLS on
+    || I1 F1 d - Fredholm1 I F m || has the same normal equations, hence the same iterates, as the time-domain MDD.
+    Checked with the oracle's restatement of the transform (pinned through the reference chain fixtures)."""
+    rng = np.random.default_rng(nt)
+    nfft = int(np.ceil((nt + 1) / 2))
+    nfmax = nfft - 2
+    ntr = 7
+    z = rng.standard_normal((nfmax, ntr)) + 1j * rng.standard_normal((nfmax, ntr))
+    z[0] = z[0].real                                   # physical spectrum: real DC
+    zp = np.zeros((nfft, ntr), dtype=complex)
+    zp[:nfmax] = z
+    t = o._fft_real_adj(zp, nt, False)
+    assert abs(np.linalg.norm(t) - np.linalg.norm(z)) <= 1e-12 * np.linalg.norm(z)
+    # and I1 F1 is its left inverse on that subspace
+    back = o._fft_real(t, nt, False)[:nfmax]
+    np.testing.assert_allclose(back, z, rtol=1e-12, atol=1e-12)
+    # with an imaginary DC component the isometry fails (the time-domain chain projects it away): documented caveat
+    z2 = z.copy()
+    z2[0] = z2[0] + 1j
+    zp[:nfmax] = z2
+    assert np.linalg.norm(o._fft_real_adj(zp, nt, False)) < np.linalg.norm(z2)
