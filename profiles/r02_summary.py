@@ -49,7 +49,7 @@ def main():
                   "L2 MB | regs | grid x block | dyn smem |\n|---|---|---|---|---|---|---|---|---|---|---|")
         for i, d in enumerate(read_report(rep)):
             def g(k, f=lambda v, u: v):
-                return f(*d[k]) if k in d else "n/a"
+                return f(*d[k]) if k in d else float("nan")
             md.append(f"| {i} `{d['kernel'][:40]}` | {g('duration', to_us):.2f} | {g('dram_read', to_bytes) / 1e6:.1f} | "
                       f"{g('dram_write', to_bytes) / 1e6:.1f} | {g('dram_pct_of_ncu_peak')} | {g('tensor_pipe_pct')} | "
                       f"{g('warps_active_pct')} | {g('l2_bytes', to_bytes) / 1e6:.1f} | {g('regs')} | {g('grid')} x {g('block')} | "

@@ -361,9 +361,9 @@ __global__ void pack_g_kernel(const float* __restrict__ G, unsigned short* __res
 // per apply: planes of X'^T,  BT[s][p][n'][k'] (k' < kpad; columns in [kp, kpad) are written as zeros)
 //   complex: n' = 2z+d, k' = 2k+c:  (c,d) = (0,0) re, (1,0) -im, (0,1) im, (1,1) re
 //   real   : n' = z,    k' = k
-// One 1024-thread block per (32-column strip of x, slice): h2 first takes every COLUMN's amax over k (power-of-two
-// scale per column, its inverse goes to invB for the epilogue), then 128 x 32 tiles are transposed through shared
-// memory and written as 16-byte (complex) / 8-byte (real) vectors along k'.
+// One 1024-thread block per (32-column strip of x, slice, 128-row tile of k): h2 first takes every COLUMN's amax over
+// all k (power-of-two scale per column, its inverse goes to invB for the epilogue), then the 128 x 32 tile is
+// transposed through shared memory and written as 16-byte (complex) / 8-byte (real) vectors along k'.
 constexpr uint32_t PK_THREADS = 1024, PK_ROWS = 128;
 template <bool CX, int MODE>
 __global__ void __launch_bounds__(PK_THREADS)
@@ -397,7 +397,7 @@ pack_x_kernel(const float* __restrict__ x, unsigned short* __restrict__ BT, floa
       float sc, inv;
       pow2_scale(m, &sc, &inv);
       scale_s[tx] = sc;
-      if (z < nz) invB[(size_t)s * nz + z] = inv;
+      if (z < nz && blockIdx.z == 0) invB[(size_t)s * nz + z] = inv;
     }
     __syncthreads();
   }
@@ -405,8 +405,10 @@ pack_x_kernel(const float* __restrict__ x, unsigned short* __restrict__ BT, floa
   unsigned short* base = BT + (size_t)s * NPL * plane;
   const uint32_t zz = threadIdx.x >> 5, kq = threadIdx.x & 31;     // write phase: one z, four consecutive k
   const float scale = MODE == MODE_H2 ? scale_s[zz] : 1.f;
-  const uint32_t kcover = kpad / (CX ? 2 : 1);                     // k values whose k' columns exist (incl. padding)
-  for (uint32_t k0 = 0; k0 < kcover; k0 += PK_ROWS) {
+  // blockIdx.z selects ONE 128-row tile of k (the column scales above are recomputed by every k-block: a few L2
+  // reads per thread, in exchange for twice the CTAs in flight on the config-5 shape)
+  {
+    const uint32_t k0 = blockIdx.z * PK_ROWS;
     for (uint32_t kk = ty; kk < PK_ROWS; kk += 32) {
       const uint32_t k = k0 + kk, z = z0 + tx;
       float2 v = make_float2(0.f, 0.f);
@@ -615,9 +617,11 @@ static int fredholm_apply_impl(b2_fredholm_plan* pl, const void* x, void* y, voi
   const int d = adjoint ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
   const uint32_t K = (uint32_t)(d == 0 ? pl->ny : pl->nx);
-  dim3 grid(pl->nstrips, (unsigned)pl->nsl);
-  const float* xf = (const float*)x;
   const uint32_t nz = (uint32_t)pl->nz, kpad = (uint32_t)pl->kpad[d];
+  const uint32_t kcover = kpad / (pl->cx ? 2u : 1u);          // k values whose k' columns exist (incl. padding)
+  dim3 grid(pl->nstrips, (unsigned)pl->nsl, (kcover + PK_ROWS - 1) / PK_ROWS);
+  if (grid.z > 65535u) return B2_ERR_ARG;
+  const float* xf = (const float*)x;
   if (parts & 1) {
     if (pl->mode == MODE_B3) {
       if (pl->cx) pack_x_kernel<true, MODE_B3><<<grid, PK_THREADS, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);

@@ -206,8 +206,9 @@ class CG(Solver):
         if self._gen:
             return self._step_generic(x)
         Opc = self.Op.matvec(self.c)
-        cOpc = float(np.abs(self.c.dot(Opc.conj())).item())
-        a = float(self.kold / cOpc)
+        cOpc = np.abs(self.c.dot(Opc.conj()))
+        with np.errstate(divide="ignore", invalid="ignore"):      # the reference divides NumPy scalars: inf / nan, no raise
+            a = float((np.float64(self.kold) / cOpc).item())
         x.axpy_(a, self.c)
         self.r.axpy_(-a, Opc)
         k = _self_dots([self.r])[0]
@@ -429,6 +430,7 @@ class CGLS(Solver):
 
         use_graph = os.environ.get("B2_CGLS_GRAPH", "1") != "0" and _graph_safe(self.Op)
         state = {"graph": None, "use": use_graph, "warm": 0}
+        self.graph_replays, self.graph_error = 0, (None if use_graph else "operator not on the graph-safe list")
         self._cc_ready = False                      # first body computes c.c itself
 
         def one():
@@ -439,11 +441,16 @@ class CGLS(Solver):
                     with torch.cuda.graph(g):          # records only: nothing executes during capture
                         self._body(x, hist, it_dev)
                     state["graph"] = g
-                except Exception:
-                    state["use"] = False               # not capturable (host sync inside an operator ...): stay eager
+                    self.graph_replays = 0
+                except Exception as exc:               # not capturable (host sync inside an operator ...): stay eager
+                    state["use"] = False
+                    self.graph_error = repr(exc)[:300]
+                    if os.environ.get("B2_CGLS_DEBUG"):
+                        print(f"[b200 cgls] CUDA-graph capture failed, running eagerly: {self.graph_error}", file=sys.stderr)
                     torch.cuda.synchronize()
             if state["graph"] is not None:
                 state["graph"].replay()
+                self.graph_replays += 1
             else:
                 self._body(x, hist, it_dev)
                 state["warm"] += 1

@@ -502,9 +502,9 @@ def test_cg_with_float64_x0_and_float32_operator(pm):
     xt = np.random.default_rng(6).standard_normal(n)
     y = Op @ pm.DistributedArray.to_dist(xt.astype(np.float32))
     x0 = pm.DistributedArray.to_dist(np.zeros(n))   # float64
-    xinv, iit, cost = pm.cg(Op, y, x0=x0, niter=40, tol=0.0)
+    xinv, iit, cost = pm.cg(Op, y, x0=x0, niter=12, tol=0.0)
     np.testing.assert_allclose(host(xinv.asarray()), xt, rtol=0, atol=1e-4 * np.abs(xt).max())
-    xinv2, *_ = pm.cgls(Op, y, x0=x0, niter=60, tol=0.0)
+    xinv2, *_ = pm.cgls(Op, y, x0=x0, niter=25, tol=0.0)
     np.testing.assert_allclose(host(xinv2.asarray()), xt, rtol=0, atol=1e-3 * np.abs(xt).max())
 
 
