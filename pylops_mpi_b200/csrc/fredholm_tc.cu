@@ -220,11 +220,30 @@ fredholm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (MODE == MODE_H2) {
           // undo the power-of-two operand scales (exact: per output row of op(G), per column of x) and the 2^11
           // of the correction terms
+          const uint32_t zc = col0 / zdiv, nzc = 32 / zdiv;          // nzc distinct column scales in this chunk
+          const float* sb_inv = invB + (size_t)s * nz + zc;
+          float cs[32];
+          if (zc + nzc <= nz && ((reinterpret_cast<uintptr_t>(sb_inv) & 15u) == 0)) {
 #pragma unroll
-          for (uint32_t j = 0; j < 32; ++j) {
-            const uint32_t z = (col0 + j) / zdiv;
-            const float sc = sa_inv * (z < nz ? __ldg(&invB[(size_t)s * nz + z]) : 0.f);
-            v[j] = __float_as_uint(fmaf(__uint_as_float(w[j]), 1.f / 2048.f, __uint_as_float(v[j])) * sc);
+            for (uint32_t t = 0; t < 32; t += 4) {                   // 16-byte broadcast loads (same address in every lane)
+              if (t < nzc) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(sb_inv + t));
+                cs[t] = q.x; cs[t + 1] = q.y; cs[t + 2] = q.z; cs[t + 3] = q.w;
+              }
+            }
+          } else {
+#pragma unroll
+            for (uint32_t t = 0; t < 32; ++t)
+              if (t < nzc) cs[t] = (zc + t < nz) ? __ldg(sb_inv + t) : 0.f;
+          }
+          if (zdiv == 2) {                                             // complex: columns (re, im) share a scale
+#pragma unroll
+            for (uint32_t j = 0; j < 32; ++j)
+              v[j] = __float_as_uint(fmaf(__uint_as_float(w[j]), 1.f / 2048.f, __uint_as_float(v[j])) * (sa_inv * cs[j >> 1]));
+          } else {
+#pragma unroll
+            for (uint32_t j = 0; j < 32; ++j)
+              v[j] = __float_as_uint(fmaf(__uint_as_float(w[j]), 1.f / 2048.f, __uint_as_float(v[j])) * (sa_inv * cs[j]));
           }
         } else {
 #pragma unroll
