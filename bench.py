@@ -619,7 +619,18 @@ def run_extras(pm, L, comm, peaks, args):
     if size > 1:
         dt = comm.allreduce(dt, "max")
     err = (xinv - xt).norm()[0] / xt.norm()[0]
+    # steady-state cost of one iteration: slope between a 50- and a 450-iteration solve (the 50-iteration wall time
+    # also carries setup, two eager warm-up iterations and the one-off graph capture)
+    torch.cuda.synchronize()
+    comm.Barrier()
+    t0 = time.perf_counter()
+    pm.CGLS(Op).solve(yd, x0=x0, niter=450, tol=0.0)
+    torch.cuda.synchronize()
+    dt2 = time.perf_counter() - t0
+    if size > 1:
+        dt2 = comm.allreduce(dt2, "max")
     out["cgls_blockdiag_4096_f32_50it"] = {"iters_per_s": 50 / dt, "ms_per_iter": dt / 50 * 1e3, "rel_err_vs_xtrue": float(err),
+                                           "ms_per_iter_steady_state": (dt2 - dt) / 400 * 1e3,
                                            "cuda_graph_replays": getattr(solver, "graph_replays", 0),
                                            "cuda_graph_error": getattr(solver, "graph_error", None)}
     # HBM-bound GEMV (A = 1 GiB)

@@ -437,9 +437,21 @@ class CGLS(Solver):
             """one iteration: eager for the first two (lazy workspaces, communicators), then captured once and replayed"""
             if state["graph"] is None and state["use"] and state["warm"] >= 2:
                 try:
+                    # manual capture on a side stream (torch.cuda.graph() would add a device synchronise, a
+                    # gc.collect() and an empty_cache() -- milliseconds, comparable to a whole 50-iteration solve)
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):          # records only: nothing executes during capture
-                        self._body(x, hist, it_dev)
+                    main = torch.cuda.current_stream()
+                    if state.get("stream") is None:
+                        state["stream"] = torch.cuda.Stream()
+                    side = state["stream"]
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        g.capture_begin()              # records only: nothing executes during capture
+                        try:
+                            self._body(x, hist, it_dev)
+                        finally:
+                            g.capture_end()
+                    main.wait_stream(side)
                     state["graph"] = g
                     self.graph_replays = 0
                 except Exception as exc:               # not capturable (host sync inside an operator ...): stay eager
