@@ -269,7 +269,9 @@ class CGLS(Solver):
         self.q = self.Op.matvec(self.c)
         self.kold = _self_dots([r])[0]
         # device-resident scalars for the fused step: [qq, cc | k, ss, xx | a, b | kold] (x2 if complex)
-        self._st = 2 if x._tdtype.is_complex else 1
+        # slot stride of the packed device scalars: (re, im) pairs as soon as ANY of the arrays is complex (a real
+        # model with complex-typed data, as in MPIMDC, must not let a complex dot spill into its neighbour's slot)
+        self._st = 2 if (x._tdtype.is_complex or self.s._tdtype.is_complex or self.c._tdtype.is_complex) else 1
         self._dev = torch.zeros(16, dtype=torch.float64, device=x.local_array.device)
         self._dev[14] = self.kold
         self.cost = []
