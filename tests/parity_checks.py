@@ -225,7 +225,7 @@ def run_all(pm, comm, full_size: bool = True):
         for (Pr, Pc) in [(g, P // g) for g in range(1, P + 1) if P % g == 0]:
             L = Pr * Pc // math.gcd(Pr, Pc)
             # ragged N and K (zero-padding paths) whose padded tiles stay 8-aligned; M / Pc % 32 == 0
-            N, K, M = 64 * Pr - (3 if Pr > 1 else 0), 128 * L - (5 if L > 1 else 0), 64 * Pc
+            N, K, M = 64 * Pr - (1 if Pr > 1 else 0), 128 * L - (1 if L > 1 else 0), 64 * Pc
             bn, bm = math.ceil(N / Pr), math.ceil(M / Pc)
             Kp = math.ceil(K / L) * L
             bkA, bkX = Kp // Pc, Kp // Pr
