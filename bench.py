@@ -632,6 +632,7 @@ def run_extras(pm, L, comm, peaks, args):
     out["cgls_blockdiag_4096_f32_50it"] = {"iters_per_s": 50 / dt, "ms_per_iter": dt / 50 * 1e3, "rel_err_vs_xtrue": float(err),
                                            "ms_per_iter_steady_state": (dt2 - dt) / 400 * 1e3,
                                            "cuda_graph_replays": getattr(solver, "graph_replays", 0),
+                                           "cuda_graph_capture_ms": getattr(solver, "graph_capture_ms", None),
                                            "cuda_graph_error": getattr(solver, "graph_error", None)}
     # HBM-bound GEMV (A = 1 GiB)
     A2 = torch.randn(32768, 8192, device="cuda")

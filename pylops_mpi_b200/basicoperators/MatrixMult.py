@@ -133,6 +133,13 @@ def tile_product(A: torch.Tensor, X: torch.Tensor, Y: torch.Tensor, op: int, acc
                 _lib.check(_lib.lib.b2_gemv(ctx, A.data_ptr(), n_a, m_a, n_a, X.data_ptr(), Y.data_ptr(),
                                             op, _lib.BF16, _lib.F32, st), "b2_gemv")
             return Y
+        if n_a % 8 or ncol % 8 or A.data_ptr() % 16 or X.data_ptr() % 16:
+            # tile extents the TMA descriptors cannot address (row pitch not a multiple of 16 bytes): rare ragged
+            # case -> float32 SIMT product of the same bf16-rounded A (float32 accumulate, X not re-rounded)
+            Xf = X if X.dtype is torch.float32 else X.float()
+            _lib.check(_lib.lib.b2_gemm(ctx, A.float().contiguous().data_ptr(), n_a, Xf.data_ptr(), ncol, Y.data_ptr(), ncol,
+                                        m, ncol, k, op, int(accumulate), _lib.F32, st), "b2_gemm")
+            return Y
         Xb = X if X.dtype is torch.bfloat16 else _cast_bf16(X)
         _lib.check(_lib.lib.b2_gemm_bf16(ctx, A.data_ptr(), n_a, Xb.data_ptr(), ncol, Y.data_ptr(), ncol,
                                          m, ncol, k, op, int(accumulate), st), "b2_gemm_bf16")

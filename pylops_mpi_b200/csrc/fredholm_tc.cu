@@ -63,7 +63,8 @@ struct Cfg {
   static constexpr uint32_t STAGES = (192u * 1024u) / STAGE_BYTES;  // 192 KB operand ring: 2/4 (b3), 3/6 (h2)
   static constexpr uint32_t SBO = 8 * BK * 2;                       // 8 rows of one swizzle span
   static constexpr uint64_t LAYOUT = (BK == 64) ? 2 : 4;            // SWIZZLE_128B : SWIZZLE_64B
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr size_t STAGING_BYTES = 4 * 32 * 33 * sizeof(float);   // epilogue transpose: [warp][32 rows][33]
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + STAGING_BYTES;
 };
 
 struct PeerOut {
@@ -84,7 +85,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 fredholm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    float* __restrict__ Y, const PeerOut peers, const float* __restrict__ invA,
                    const float* __restrict__ invB, uint32_t nz, uint32_t zdiv, uint32_t nsl, uint32_t m,
-                   uint32_t n, uint32_t kpad, uint32_t n_umma, int vec_ok, int concat) {
+                   uint32_t n, uint32_t kpad, uint32_t n_umma, int vec_ok, int concat, int staged) {
   using C = Cfg<MODE, BK>;
   constexpr uint32_t NPL = C::NPL;
   extern __shared__ uint8_t smem_raw[];
@@ -94,6 +95,7 @@ fredholm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* tmem_full_bar = empty_bar + C::STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* stage_all = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t num_m = (m + BM - 1) / BM, num_n = (n + BN - 1) / BN;
@@ -249,27 +251,43 @@ fredholm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
           for (uint32_t j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
         }
-        if (row < m && col0 < n) {
-          const size_t off = roff + col0;
-          if (vec_ok && col0 + 32 <= n) {
+        // Transpose the 32 x 32 chunk through shared memory so that every store instruction writes ONE full 128-byte
+        // line of ONE row (lane = column): the TMEM layout (lane = row) would give 32 scattered 16-byte pieces per
+        // instruction -- tolerable in local HBM, but over NVLink (fused all-gather into the peers' outputs) 16-byte
+        // writes waste most of every packet.
+        if (!staged) {
+          // single-GPU default: direct 16-byte stores of this thread's row piece
+          if (row < m && col0 < n) {
+            const size_t off = roff + col0;
+            if (vec_ok && col0 + 32 <= n) {
 #pragma unroll
-            for (uint32_t j = 0; j < 32; j += 4) {
-              const float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                           __uint_as_float(v[j + 3]));
-              *reinterpret_cast<float4*>(Y + off + j) = o;
-              for (int d = 0; d < peers.n; ++d) *reinterpret_cast<float4*>(peers.p[d] + off + j) = o;
-            }
-          } else {
+              for (uint32_t j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(Y + off + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                     __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
 #pragma unroll
-            for (uint32_t j = 0; j < 32; ++j) {
-              if (col0 + j < n) {
-                const float o = __uint_as_float(v[j]);
-                Y[off + j] = o;
-                for (int d = 0; d < peers.n; ++d) peers.p[d][off + j] = o;
-              }
+              for (uint32_t j = 0; j < 32; ++j)
+                if (col0 + j < n) Y[off + j] = __uint_as_float(v[j]);
             }
           }
+          continue;
         }
+        float* stg = stage_all + (warp - 2) * (32 * 33);
+#pragma unroll
+        for (uint32_t j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+        __syncwarp();
+        const uint32_t ccol = col0 + lane;
+        if (ccol < n) {
+          const uint32_t row_w0 = m_blk * BM + g * 32;
+          const uint32_t nrow = row_w0 < m ? (m - row_w0 < 32 ? m - row_w0 : 32) : 0;
+          size_t off = ((size_t)s * m + row_w0) * n + ccol;
+          for (uint32_t r = 0; r < nrow; ++r, off += n) {
+            const float o = stg[r * 33 + lane];
+            Y[off] = o;
+            for (int d = 0; d < peers.n; ++d) peers.p[d][off] = o;
+          }
+        }
+        __syncwarp();
       }
       tcgen05_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
@@ -503,6 +521,7 @@ struct b2_fredholm_plan {
                                     // direction), inverse scale per (slice, column of x)
   uint32_t n, n_umma, nstrips;  // output columns (real), UMMA N, 32-column strips of x
   int concat;                   // fp16x2 with full 128-column tiles: hi_a x [hi_b | lo_b] as one N = 256 MMA
+  int stage_always;             // B2_FREDHOLM_STAGE=1: coalescing epilogue also without peers (default: only with peers)
   CUtensorMap tmA[2], tmB[2];
 };
 
@@ -541,6 +560,8 @@ extern "C" int b2_fredholm_plan_create(b2_ctx* ctx, const void* G, size_t nsl, s
     pl->mode = (mo && (mo[0] == 'b' || mo[0] == 'B')) ? MODE_B3 : MODE_H2;
     const char* cc = getenv("B2_FREDHOLM_CONCAT");
     pl->concat = cc ? atoi(cc) : 1;
+    const char* sg = getenv("B2_FREDHOLM_STAGE");
+    pl->stage_always = sg ? atoi(sg) : 0;
   }
   const uint32_t npl = npl_of(pl->mode);
   const size_t mul = pl->cx ? 2 : 1;
@@ -623,7 +644,8 @@ static int launch_product(b2_fredholm_plan* pl, int d, float* y, const PeerOut& 
   cfg.numAttrs = 1;
   B2_CUDA(cudaLaunchKernelEx(&cfg, fredholm_tc_kernel<MODE, BK>, pl->tmA[d], pl->tmB[d], y, po, (const float*)pl->invA[d],
                              (const float*)pl->invB, (uint32_t)pl->nz, pl->cx ? 2u : 1u, (uint32_t)pl->nsl, m, pl->n,
-                             (uint32_t)pl->kpad[d], pl->n_umma, vec_ok, pl->concat));
+                             (uint32_t)pl->kpad[d], pl->n_umma, vec_ok, pl->concat,
+                             (po.n > 0 || pl->stage_always) ? 1 : 0));
   return B2_OK;
 }
 

@@ -20,6 +20,7 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t NUM_THREADS = 192;
 constexpr uint32_t GROUP_M = 4;                           // in units of 256-row cluster tiles
 constexpr size_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+constexpr size_t SMEM_BYTES_SEG = SMEM_BYTES + 4 * 32 * 33 * sizeof(float);   // + epilogue transpose staging
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -271,14 +272,25 @@ gemm_bf16_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         size_t col0 = (size_t)tc.n_blk * BN + c0;
         const bool in_range = row < m && col0 < n;
         if constexpr (SEG) {
-          if (in_range) {      // this 32-column chunk lies inside ONE segment (seg_cols % 32 == 0)
+          // Segmented output = (mostly) PEER memory: transpose the 32 x 32 chunk through shared memory so that each
+          // store instruction writes one full 128-byte line of one row (lane = column) -- 16-byte pieces scattered
+          // over 32 rows waste most of every NVLink packet (measured: stationary-A at 0.62 of peak with direct stores).
+          float* stg = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * (32 * 33);
+#pragma unroll
+          for (uint32_t j = 0; j < 32; ++j) stg[lane * 33 + j] = __uint_as_float(v[j]);
+          __syncwarp();
+          if (col0 < n) {      // this 32-column chunk lies inside ONE segment (seg_cols % 32 == 0)
             const uint32_t sidx = (uint32_t)(col0 / seg.seg_cols);
-            crow = seg.base[sidx] + row * ldc;
-            col0 -= (size_t)sidx * seg.seg_cols;
+            const size_t row_w0 = (size_t)tc.m_blk * 2 * BM + cta_rank * BM + g * 32;
+            const uint32_t nrow = row_w0 < m ? (uint32_t)((m - row_w0 < 32) ? m - row_w0 : 32) : 0u;
+            float* dst = seg.base[sidx] + row_w0 * ldc + (col0 - (size_t)sidx * seg.seg_cols) + lane;
+            for (uint32_t r = 0; r < nrow; ++r, dst += ldc) *dst = stg[r * 33 + lane];
           }
+          __syncwarp();
+          continue;
         }
         if (in_range) {
-          const size_t nlim = SEG ? (size_t)seg.seg_cols : (size_t)n;     // SEG: n is a whole number of segments
+          const size_t nlim = (size_t)n;
           if (vec_ok && col0 + 32 <= nlim) {
 #pragma unroll
             for (uint32_t j = 0; j < 32; j += 4) {
@@ -409,17 +421,17 @@ extern "C" int b2_gemm_bf16_seg(b2_ctx* ctx, const void* A, size_t lda, const vo
   static bool attr_set[2] = {false, false};
   if (a_mn) {
     if (!attr_set[1]) {
-      B2_CUDA(cudaFuncSetAttribute(gemm_bf16_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+      B2_CUDA(cudaFuncSetAttribute(gemm_bf16_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_SEG));
       attr_set[1] = true;
     }
-    gemm_bf16_tc2_kernel<true, true><<<2 * clusters, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, nullptr, ldc, (uint32_t)m, (uint32_t)n,
+    gemm_bf16_tc2_kernel<true, true><<<2 * clusters, NUM_THREADS, SMEM_BYTES_SEG, st>>>(tmA, tmB, nullptr, ldc, (uint32_t)m, (uint32_t)n,
                                                                                     (uint32_t)k, 0, 1, so);
   } else {
     if (!attr_set[0]) {
-      B2_CUDA(cudaFuncSetAttribute(gemm_bf16_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+      B2_CUDA(cudaFuncSetAttribute(gemm_bf16_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES_SEG));
       attr_set[0] = true;
     }
-    gemm_bf16_tc2_kernel<false, true><<<2 * clusters, NUM_THREADS, SMEM_BYTES, st>>>(tmA, tmB, nullptr, ldc, (uint32_t)m, (uint32_t)n,
+    gemm_bf16_tc2_kernel<false, true><<<2 * clusters, NUM_THREADS, SMEM_BYTES_SEG, st>>>(tmA, tmB, nullptr, ldc, (uint32_t)m, (uint32_t)n,
                                                                                      (uint32_t)k, 0, 1, so);
   }
   B2_LAUNCH_CHECK();

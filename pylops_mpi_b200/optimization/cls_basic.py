@@ -438,6 +438,7 @@ class CGLS(Solver):
         def one():
             """one iteration: eager for the first two (lazy workspaces, communicators), then captured once and replayed"""
             if state["graph"] is None and state["use"] and state["warm"] >= 2:
+                t_cap = time.perf_counter()
                 try:
                     # manual capture on a side stream (torch.cuda.graph() would add a device synchronise, a
                     # gc.collect() and an empty_cache() -- milliseconds, comparable to a whole 50-iteration solve)
@@ -456,6 +457,7 @@ class CGLS(Solver):
                     main.wait_stream(side)
                     state["graph"] = g
                     self.graph_replays = 0
+                    self.graph_capture_ms = (time.perf_counter() - t_cap) * 1e3
                 except Exception as exc:               # not capturable (host sync inside an operator ...): stay eager
                     state["use"] = False
                     self.graph_error = repr(exc)[:300]

@@ -524,7 +524,8 @@ def test_real_block_applied_to_complex_data_keeps_imaginary_part(pm):
     xv = rng.standard_normal(22)
     y2 = Op2 @ pm.DistributedArray.to_dist(xv)
     assert y2.dtype == np.float64
-    np.testing.assert_allclose(host(y2.asarray()), np.concatenate([A @ xv[:17], B32.astype(np.float64) @ xv[17:]]), rtol=1e-6)
+    np.testing.assert_allclose(host(y2.asarray()), np.concatenate([A @ xv[:17], B32.astype(np.float64) @ xv[17:]]),
+                               rtol=1e-5, atol=1e-5)          # the float32 block runs a float32 GEMV
 
 
 def test_local_operator_typeerror_is_not_swallowed(pm):
