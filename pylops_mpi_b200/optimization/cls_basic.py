@@ -395,8 +395,8 @@ class CGLS(Solver):
                                             _lib.stream()), "b2_history_push")
 
     def _run_blocks(self, x, niter: int):
-        """remaining iterations in blocks: the body is captured ONCE in a CUDA graph (after two eager warm-up
-        iterations) and replayed; the host reads the scalar history once per block.  With tol > 0 a block is at
+        """remaining iterations in blocks: the body is captured ONCE in a CUDA graph (after one eager warm-up
+        iteration) and replayed; the host reads the scalar history once per block.  With tol > 0 a block is at
         most 8 iterations and is re-run from a checkpoint up to the stopping iteration, so x, cost and the
         iteration count are exactly those of the reference's per-iteration test ``kold > tol`` (cls_basic.py:436)."""
         import os
@@ -436,8 +436,9 @@ class CGLS(Solver):
         self._cc_ready = False                      # first body computes c.c itself
 
         def one():
-            """one iteration: eager for the first two (lazy workspaces, communicators), then captured once and replayed"""
-            if state["graph"] is None and state["use"] and state["warm"] >= 2:
+            """one iteration: the first runs eagerly (every kernel of the body gets loaded, lazy workspaces and
+            communicators exist), then the body is captured once and replayed"""
+            if state["graph"] is None and state["use"] and state["warm"] >= 1:
                 t_cap = time.perf_counter()
                 try:
                     # manual capture on a side stream (torch.cuda.graph() would add a device synchronise, a
