@@ -3,5 +3,4 @@
 mkdir -p gpurun_out
 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29622 bench.py --gpus 8 --steps 20 --warmup 5 > gpurun_out/r02_bench_n8.json 2> gpurun_out/r02_bench_n8.err; echo "bench8_rc=$?" >> gpurun_out/r02_bench_n8.err
 B2_PARITY_FULL=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29621 tests/multi_worker.py > gpurun_out/r02_multi8.log 2>&1; echo "multi8_rc=$?" >> gpurun_out/r02_multi8.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29623 bench.py --gpus 4 --steps 20 --warmup 5 > gpurun_out/r02_bench_n4.json 2> gpurun_out/r02_bench_n4.err; echo "bench4_rc=$?" >> gpurun_out/r02_bench_n4.err
-tail -n 4 gpurun_out/r02_bench_n8.err; cut -c1-600 gpurun_out/r02_bench_n8.json; grep "MULTI_WORKER\|multi8_rc\|Error" gpurun_out/r02_multi8.log | head -12; tail -n 2 gpurun_out/r02_bench_n4.err
+tail -n 4 gpurun_out/r02_bench_n8.err; cut -c1-600 gpurun_out/r02_bench_n8.json; grep "MULTI_WORKER\|multi8_rc\|Error" gpurun_out/r02_multi8.log | head -12
