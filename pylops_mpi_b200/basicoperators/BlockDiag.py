@@ -48,13 +48,15 @@ class MPIBlockDiag(MPILinearOperator):
     @reshaped(forward=True, stacking=True)
     def _matvec(self, x: DistributedArray) -> DistributedArray:
         y = DistributedArray(global_shape=self.shape[0], base_comm=x.base_comm,
-                             local_shapes=self.local_shapes_n, mask=self.mask, dtype=self.dtype)
+                             local_shapes=self.local_shapes_n, mask=self.mask, dtype=self.dtype,
+                             _trusted=True)       # shapes validated once at construction
         _apply_ops(self.ops, x.local_array, self.mmops, y.local_array, self.nnops, False)
         return y
 
     @reshaped(forward=False, stacking=True)
     def _rmatvec(self, x: DistributedArray) -> DistributedArray:
         y = DistributedArray(global_shape=self.shape[1], base_comm=x.base_comm,
-                             local_shapes=self.local_shapes_m, mask=self.mask, dtype=self.dtype)
+                             local_shapes=self.local_shapes_m, mask=self.mask, dtype=self.dtype,
+                             _trusted=True)
         _apply_ops(self.ops, x.local_array, self.nnops, y.local_array, self.mmops, True)
         return y

@@ -349,7 +349,7 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
         rows_out, full_out = (bkX, self.K) if adjoint else (bn, self.N)
         y = DistributedArray(global_shape=(full_out * self.M), mask=x.mask,
                              local_shapes=self._tile_sizes(rows_out, full_out), partition=Partition.SCATTER,
-                             dtype=torch.float32, base_comm=x.base_comm)
+                             dtype=torch.float32, base_comm=x.base_comm, _trusted=True)
         x_block, _, local_m = self._padded_block(x, rows_in, full_in, torch.float32)
         local_out = self._extent(rows_out, full_out, i, Pr)
 
@@ -446,7 +446,7 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
         rows_out, full_out = (bkX, self.K) if adjoint else (self._bn, self.N)
         y = DistributedArray(global_shape=(full_out * self.M), mask=x.mask,
                              local_shapes=self._tile_sizes(rows_out, full_out), partition=Partition.SCATTER,
-                             dtype=xdt, base_comm=x.base_comm)
+                             dtype=xdt, base_comm=x.base_comm, _trusted=True)
         x_block, _, local_m = self._padded_block(x, rows_in, full_in, xdt)
         if self._A_row.dtype is torch.bfloat16 and self._bm > 1:
             x_block = _cast_bf16(x_block)                 # halves the allgather payload
@@ -567,7 +567,7 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
         bkX = self._w * self._px
         y = DistributedArray(global_shape=(self.N * self.M), mask=x.mask,
                              local_shapes=self._tile_sizes(self._bn, self.N), partition=Partition.SCATTER,
-                             dtype=xdt, base_comm=x.base_comm)
+                             dtype=xdt, base_comm=x.base_comm, _trusted=True)
         x_block, local_k, local_m = self._padded_block(x, bkX, self.K, xdt)
         local_n = self._extent(self._bn, self.N, self._row_id, self._Pr)
         Y_local = torch.empty((self._bn, self._bm), dtype=xdt, device=x_block.device)
@@ -607,7 +607,7 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
         bkX = self._w * self._px
         y = DistributedArray(global_shape=(self.K * self.M), mask=x.mask,
                              local_shapes=self._tile_sizes(bkX, self.K), partition=Partition.SCATTER,
-                             dtype=xdt, base_comm=x.base_comm)
+                             dtype=xdt, base_comm=x.base_comm, _trusted=True)
         x_block, local_n, local_m = self._padded_block(x, self._bn, self.N, xdt)
         local_k = self._extent(bkX, self.K, self._row_id, self._Pr)
         Y_local = torch.zeros((bkX, self._bm), dtype=xdt, device=x_block.device)

@@ -40,7 +40,7 @@ class MPIVStack(MPILinearOperator):
             raise ValueError(f"x should have partition={Partition.BROADCAST},{Partition.UNSAFE_BROADCAST}"
                              f"Got  {x.partition} instead...")
         y = DistributedArray(global_shape=self.shape[0], base_comm=x.base_comm,
-                             local_shapes=self.local_shapes_n, dtype=self.dtype)
+                             local_shapes=self.local_shapes_n, dtype=self.dtype, _trusted=True)
         for iop, oper in enumerate(self.ops):
             oi = y.local_array[self.nnops[iop]:self.nnops[iop + 1]]
             apply_into(oper, x.local_array, oi, False)
