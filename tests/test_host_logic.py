@@ -271,3 +271,20 @@ def test_strict_parity_mode_raises_exactly_where_the_reference_does(dims, P):
             D._strict_check(x, dst)
     else:
         D._strict_check(x, dst)
+
+
+def test_cgls_graph_whitelist_is_conservative():
+    """CGLS replays its iteration as a CUDA graph only for operator trees made of whitelisted classes; anything unknown
+    (user operators, MPIFredholm1's host-toggled fused mode, MDC's FFT wrappers) keeps the eager path"""
+    from pylops_mpi_b200.optimization.cls_basic import _graph_safe
+
+    def make(name, **attrs):
+        return type(name, (), {"shape": (4, 4), **attrs})()
+    blk = make("MatrixMult")
+    assert _graph_safe(make("MPIBlockDiag", ops=[blk]))
+    assert _graph_safe(make("_ProductLinearOperator", args=(make("MPIBlockDiag", ops=[blk]), make("MPIFirstDerivative"))))
+    assert _graph_safe(make("_ScaledLinearOperator", args=(make("MPIVStack", ops=[blk]), 2.0)))
+    assert not _graph_safe(make("MPIFredholm1"))
+    assert not _graph_safe(make("MPILinearOperator"))                       # wrapper of an arbitrary local operator
+    assert not _graph_safe(make("MPIBlockDiag", ops=[make("SomeUserOperator")]))
+    assert not _graph_safe(make("_SumLinearOperator", args=(make("MPIBlockDiag", ops=[blk]), make("MPIFredholm1"))))
