@@ -50,6 +50,15 @@ _GRAPH_SAFE_TYPES = ("MPIBlockDiag", "MPIVStack", "MPIHStack", "MPIFirstDerivati
                      "MatrixMult", "FirstDerivative", "SecondDerivative")
 
 
+_GRAPH_POOL = []
+
+
+def _graph_pool():
+    if not _GRAPH_POOL:
+        _GRAPH_POOL.append(torch.cuda.graph_pool_handle())
+    return _GRAPH_POOL[0]
+
+
 def _graph_safe(Op) -> bool:
     """may an apply of ``Op`` be captured once in a CUDA graph and replayed?  Conservative whitelist: operators of
     this package whose apply is a fixed sequence of kernel launches / collectives with no host-side per-call state
@@ -450,7 +459,10 @@ class CGLS(Solver):
                     side = state["stream"]
                     side.wait_stream(main)
                     with torch.cuda.stream(side):
-                        g.capture_begin()              # records only: nothing executes during capture
+                        # one process-wide memory pool for all captures: the temporaries of the first capture are
+                        # cudaMalloc'ed (slow when peers have this device mapped: measured 3.1 ms at 2 GPUs vs 0.65 ms
+                        # at 1), later captures reuse the cached blocks
+                        g.capture_begin(pool=_graph_pool())   # records only: nothing executes during capture
                         try:
                             self._body(x, hist, it_dev)
                         finally:
