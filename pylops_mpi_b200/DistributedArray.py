@@ -91,7 +91,7 @@ class DistributedArray(DistributedMixIn):
         if len(global_shape) <= axis:
             raise IndexError(f"Axis {axis} out of range for DistributedArray "
                              f"of shape {global_shape}")
-        if partition not in Partition:
+        if not _trusted and partition not in Partition:
             raise ValueError(f"Should be either {Partition.BROADCAST}, "
                              f"{Partition.UNSAFE_BROADCAST} or {Partition.SCATTER}")
         self._tdtype = _lib.torch_dtype(dtype)
@@ -105,7 +105,8 @@ class DistributedArray(DistributedMixIn):
         self._sub_comm = self._base_comm if mask is None else subcomm_split(mask, self._base_comm)
         size, rank = self._base_comm.Get_size(), self._base_comm.Get_rank()
         if local_shapes is not None:
-            local_shapes = [_tup(s) for s in local_shapes]
+            if not (_trusted and type(local_shapes[0]) is tuple):     # operator temporaries pass validated tuples
+                local_shapes = [_tup(s) for s in local_shapes]
             if not _trusted:  # internal constructions pass shapes derived from validated arrays
                 self._check_local_shapes(local_shapes)
             self._local_shapes = local_shapes
@@ -623,8 +624,8 @@ class DistributedArray(DistributedMixIn):
     def _ravel_view(self):
         """flattened DistributedArray SHARING this array's buffer (internal: used on
         operator temporaries where the reference's ravel() copy is pure overhead)"""
-        local_shapes = [(int(np.prod(s)),) for s in self._local_shapes]
-        return DistributedArray(global_shape=int(np.prod(self._global_shape)),
+        local_shapes = [(math.prod(s),) for s in self._local_shapes]
+        return DistributedArray(global_shape=math.prod(self._global_shape),
                                 base_comm=self._base_comm, local_shapes=local_shapes,
                                 mask=self._mask, partition=self._partition, dtype=self._tdtype,
                                 _buffer=self._cont().reshape(-1), _trusted=True)

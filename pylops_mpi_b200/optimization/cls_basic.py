@@ -59,6 +59,20 @@ def _graph_pool():
     return _GRAPH_POOL[0]
 
 
+def _reset_capture_state():
+    """a capture that died half-way leaves torch's CUDA generator flagged as 'capturing' (every later RNG call then
+    raises 'Offset increment outside graph capture'): one empty, successful capture clears the flag"""
+    try:
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            g.capture_begin(capture_error_mode="thread_local")
+            g.capture_end()
+        torch.cuda.synchronize()
+    except Exception:
+        pass
+
+
 def _graph_safe(Op) -> bool:
     """may an apply of ``Op`` be captured once in a CUDA graph and replayed?  Conservative whitelist: operators of
     this package whose apply is a fixed sequence of kernel launches / collectives with no host-side per-call state
@@ -462,7 +476,10 @@ class CGLS(Solver):
                         # one process-wide memory pool for all captures: the temporaries of the first capture are
                         # cudaMalloc'ed (slow when peers have this device mapped: measured 3.1 ms at 2 GPUs vs 0.65 ms
                         # at 1), later captures reuse the cached blocks
-                        g.capture_begin(pool=_graph_pool())   # records only: nothing executes during capture
+                        # thread_local error mode: NCCL's helper threads keep polling CUDA while we capture
+                        # (observed at 8 ranks: a "global"-mode capture was invalidated and left torch's RNG state
+                        # stuck in capture mode)
+                        g.capture_begin(pool=_graph_pool(), capture_error_mode="thread_local")   # records only
                         try:
                             self._body(x, hist, it_dev)
                         finally:
@@ -474,9 +491,9 @@ class CGLS(Solver):
                 except Exception as exc:               # not capturable (host sync inside an operator ...): stay eager
                     state["use"] = False
                     self.graph_error = repr(exc)[:300]
-                    if os.environ.get("B2_CGLS_DEBUG"):
-                        print(f"[b200 cgls] CUDA-graph capture failed, running eagerly: {self.graph_error}", file=sys.stderr)
+                    print(f"[b200 cgls] CUDA-graph capture failed, running eagerly: {self.graph_error}", file=sys.stderr)
                     torch.cuda.synchronize()
+                    _reset_capture_state()
             if state["graph"] is not None:
                 state["graph"].replay()
                 self.graph_replays += 1

@@ -340,7 +340,7 @@ assert res["failed"] == 0, res["failures"]
 
 # frequency-domain MDC (scattered spectrum) at P ranks: F1^H I1^H of its gathered output == time-domain MDC
 import warnings  # noqa: E402
-nt, ns, nr, nv = 32, 5, 6, 3
+nt, ns, nr, nv = 8 * P + 8, 5, 6, 3        # one-sided: nfft = 4 P + 5 >= the 4 P slices of the band
 nfmax = 4 * P
 gt = comm.bcast(np.random.default_rng(31).standard_normal((nt, ns, nr)), 0)
 Gf = np.fft.rfft(gt, n=nt, axis=0)[:nfmax].astype(np.complex128)
