@@ -301,6 +301,17 @@ def run_gpu_arm(args):
                                   "error": "parity check failed: timing aborted"}))
             sys.exit(1)
 
+    # a CUDA-graph capture that died half-way (seen once at 8 ranks) leaves torch's generator flagged as capturing and
+    # every later RNG call raises: probe, and clear the flag with one empty capture if needed
+    try:
+        torch.empty(4, device="cuda").normal_()
+        rng_note = None
+    except RuntimeError as exc:
+        from pylops_mpi_b200.optimization.cls_basic import _reset_capture_state
+        _reset_capture_state()
+        rng_note = f"torch CUDA generator was stuck in capture mode ({repr(exc)[:80]}): reset"
+        torch.empty(4, device="cuda").normal_()
+
     # ---- inputs resident in HBM --------------------------------------------------
     g = torch.Generator(device="cuda").manual_seed(42 + rank)
     x = pm.DistributedArray(global_shape=N * NCOLS, dtype=np.float32)
@@ -444,7 +455,7 @@ def run_gpu_arm(args):
                 "e2e": e2e, "gpu_launches": args.steps * launches,
                 "halo": ("peer-memory push + flags inside the stencil kernel (1 launch / apply)" if fused_halo else
                          ("none (single rank)" if size == 1 else "grouped ncclSend/Recv on a side stream (3 launches / apply)")),
-                "clocks": clocks, "host_enqueue_ms_per_step": enqueue_ms, "parity": parity,
+                "clocks": clocks, "host_enqueue_ms_per_step": enqueue_ms, "parity": parity, "rng_note": rng_note,
                 "secondary": secondary, "extra": extra}
         print(json.dumps(line))
 
