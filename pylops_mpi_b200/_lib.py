@@ -170,12 +170,16 @@ def cpair(z):
 
 
 _CTX = {}
+_CUDA_OK = False
 
 
 def ctx(device=None):
     """per-device b2_ctx handle (created on first use; needs a CUDA device)"""
-    if not torch.cuda.is_available():
-        raise B200Error("pylops_mpi_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    global _CUDA_OK
+    if not _CUDA_OK:            # checked until it succeeds once (the check costs microseconds on a hot enqueue path)
+        if not torch.cuda.is_available():
+            raise B200Error("pylops_mpi_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        _CUDA_OK = True
     dev = torch.cuda.current_device() if device is None else int(device)
     h = _CTX.get(dev)
     if h is None:

@@ -488,6 +488,96 @@ pack_x_kernel(const float* __restrict__ x, unsigned short* __restrict__ BT, floa
   }
 }
 
+// Single-pass variant for short contractions (k' columns covered by <= PS_K values of k: config 5 has K = 256):
+// one 256-thread block per (16-column strip of x, slice) reads its whole K x 16 strip ONCE -- 16 independent loads
+// per thread in flight -- into shared memory, takes the column scales from the values it already holds and writes
+// the planes.  Versus the generic kernel above: no second read of x, a quarter of the threads per block (faster
+// block launch), 256 blocks for config 5.  Shared tile columns are rotated by k/4 so that both the row-wise fill
+// and the 4-consecutive-k reads of the write phase are bank-conflict free.
+constexpr uint32_t PS_THREADS = 256, PS_K = 256, PS_Z = 16;
+template <bool CX, int MODE>
+__global__ void __launch_bounds__(PS_THREADS)
+pack_x_small_kernel(const float* __restrict__ x, unsigned short* __restrict__ BT, float* __restrict__ invB, uint32_t K,
+                    uint32_t nz, uint32_t nrows, uint32_t kpad) {
+  constexpr uint32_t NPL = npl_of(MODE);
+  __shared__ float2 tile[PS_K][PS_Z];
+  __shared__ float colmax[PS_THREADS / PS_Z][PS_Z + 1];
+  __shared__ float scale_s[PS_Z];
+  grid_dep_launch();               // PDL: the product kernel may start its prologue / A loads now
+  const uint32_t s = blockIdx.y, z0 = blockIdx.x * PS_Z;
+  const uint32_t tx = threadIdx.x & (PS_Z - 1), ty = threadIdx.x / PS_Z;
+  const float* xs = x + (size_t)s * K * nz * (CX ? 2 : 1);
+  {
+    const uint32_t z = z0 + tx;
+    float2 v[PS_K / (PS_THREADS / PS_Z)];
+#pragma unroll
+    for (uint32_t i = 0; i < PS_K / (PS_THREADS / PS_Z); ++i) {
+      const uint32_t k = ty + (PS_THREADS / PS_Z) * i;
+      v[i] = make_float2(0.f, 0.f);
+      if (k < K && z < nz) {
+        if (CX) v[i] = reinterpret_cast<const float2*>(xs)[(size_t)k * nz + z];
+        else v[i].x = xs[(size_t)k * nz + z];
+      }
+    }
+    float am = 0.f;
+#pragma unroll
+    for (uint32_t i = 0; i < PS_K / (PS_THREADS / PS_Z); ++i) {
+      const uint32_t k = ty + (PS_THREADS / PS_Z) * i;
+      tile[k][(tx + (k >> 2)) & (PS_Z - 1)] = v[i];
+      am = fmaxf(am, fmaxf(fabsf(v[i].x), fabsf(v[i].y)));
+    }
+    if (MODE == MODE_H2) colmax[ty][tx] = am;
+  }
+  __syncthreads();
+  if (MODE == MODE_H2) {
+    if (threadIdx.x < PS_Z) {
+      float m = colmax[0][threadIdx.x];
+#pragma unroll
+      for (uint32_t i = 1; i < PS_THREADS / PS_Z; ++i) m = fmaxf(m, colmax[i][threadIdx.x]);
+      float sc, inv;
+      pow2_scale(m, &sc, &inv);
+      scale_s[threadIdx.x] = sc;
+      if (z0 + threadIdx.x < nz) invB[(size_t)s * nz + z0 + threadIdx.x] = inv;
+    }
+    __syncthreads();
+  }
+  const size_t plane = (size_t)nrows * kpad;
+  unsigned short* base = BT + (size_t)s * NPL * plane;
+#pragma unroll
+  for (uint32_t it = 0; it < PS_Z * (PS_K / 4) / PS_THREADS; ++it) {
+    const uint32_t item = threadIdx.x + PS_THREADS * it;
+    const uint32_t kq = item & (PS_K / 4 - 1), zz = item / (PS_K / 4);
+    const uint32_t z = z0 + zz, kb = 4 * kq;
+    if (z >= nz || kb * (CX ? 2 : 1) >= kpad) continue;
+    const float scale = MODE == MODE_H2 ? scale_s[zz] : 1.f;
+    Split<MODE> re[4], im[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 v = tile[kb + j][(zz + kq) & (PS_Z - 1)];
+      re[j] = split<MODE>(v.x, scale);
+      if (CX) im[j] = split<MODE>(v.y, scale);
+    }
+#pragma unroll
+    for (uint32_t p = 0; p < NPL; ++p) {
+      unsigned short* q = base + p * plane;
+      if (CX) {
+        uint4 r0, r1;      // row 2z: (re, -im) pairs; row 2z+1: (im, re) pairs
+        r0.x = re[0].p[p] | ((uint32_t)neg16(im[0].p[p]) << 16);  r1.x = im[0].p[p] | ((uint32_t)re[0].p[p] << 16);
+        r0.y = re[1].p[p] | ((uint32_t)neg16(im[1].p[p]) << 16);  r1.y = im[1].p[p] | ((uint32_t)re[1].p[p] << 16);
+        r0.z = re[2].p[p] | ((uint32_t)neg16(im[2].p[p]) << 16);  r1.z = im[2].p[p] | ((uint32_t)re[2].p[p] << 16);
+        r0.w = re[3].p[p] | ((uint32_t)neg16(im[3].p[p]) << 16);  r1.w = im[3].p[p] | ((uint32_t)re[3].p[p] << 16);
+        *reinterpret_cast<uint4*>(q + (size_t)(2 * z) * kpad + 2 * kb) = r0;
+        *reinterpret_cast<uint4*>(q + (size_t)(2 * z + 1) * kpad + 2 * kb) = r1;
+      } else {
+        uint2 r0;
+        r0.x = re[0].p[p] | ((uint32_t)re[1].p[p] << 16);
+        r0.y = re[2].p[p] | ((uint32_t)re[3].p[p] << 16);
+        *reinterpret_cast<uint2*>(q + (size_t)z * kpad + kb) = r0;
+      }
+    }
+  }
+}
+
 int make_tmap3(CUtensorMap* tm, const void* base, uint64_t kpad, uint64_t rows, uint64_t nmat, uint32_t box_k,
                uint32_t box_rows, bool fp16) {
   EncodeTiledFn fn = get_encode_fn();
@@ -521,6 +611,7 @@ struct b2_fredholm_plan {
                                     // direction), inverse scale per (slice, column of x)
   uint32_t n, n_umma, nstrips;  // output columns (real), UMMA N, 32-column strips of x
   int concat;                   // fp16x2 with full 128-column tiles: hi_a x [hi_b | lo_b] as one N = 256 MMA
+  int pack_small;               // B2_FREDHOLM_PACK_SMALL=0: always use the generic two-pass pack kernel
   int stage_always;             // B2_FREDHOLM_STAGE=1: coalescing epilogue also without peers (default: only with peers)
   CUtensorMap tmA[2], tmB[2];
 };
@@ -562,6 +653,8 @@ extern "C" int b2_fredholm_plan_create(b2_ctx* ctx, const void* G, size_t nsl, s
     pl->concat = cc ? atoi(cc) : 1;
     const char* sg = getenv("B2_FREDHOLM_STAGE");
     pl->stage_always = sg ? atoi(sg) : 0;
+    const char* ps = getenv("B2_FREDHOLM_PACK_SMALL");
+    pl->pack_small = ps ? atoi(ps) : 1;
   }
   const uint32_t npl = npl_of(pl->mode);
   const size_t mul = pl->cx ? 2 : 1;
@@ -663,7 +756,17 @@ static int fredholm_apply_impl(b2_fredholm_plan* pl, const void* x, void* y, voi
   dim3 grid(pl->nstrips, (unsigned)pl->nsl, (kcover + PK_ROWS - 1) / PK_ROWS);
   if (grid.z > 65535u) return B2_ERR_ARG;
   const float* xf = (const float*)x;
-  if (parts & 1) {
+  if ((parts & 1) && pl->pack_small && kcover <= PS_K) {
+    dim3 gs((nz + PS_Z - 1) / PS_Z, (unsigned)pl->nsl);
+    if (pl->mode == MODE_B3) {
+      if (pl->cx) pack_x_small_kernel<true, MODE_B3><<<gs, PS_THREADS, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
+      else pack_x_small_kernel<false, MODE_B3><<<gs, PS_THREADS, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
+    } else {
+      if (pl->cx) pack_x_small_kernel<true, MODE_H2><<<gs, PS_THREADS, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
+      else pack_x_small_kernel<false, MODE_H2><<<gs, PS_THREADS, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
+    }
+    B2_LAUNCH_CHECK();
+  } else if (parts & 1) {
     if (pl->mode == MODE_B3) {
       if (pl->cx) pack_x_kernel<true, MODE_B3><<<grid, PK_THREADS, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);
       else pack_x_kernel<false, MODE_B3><<<grid, PK_THREADS, 0, st>>>(xf, pl->BT[d], pl->invB, K, nz, pl->n, kpad);

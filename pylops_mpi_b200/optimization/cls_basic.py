@@ -50,13 +50,31 @@ _GRAPH_SAFE_TYPES = ("MPIBlockDiag", "MPIVStack", "MPIHStack", "MPIFirstDerivati
                      "MatrixMult", "FirstDerivative", "SecondDerivative")
 
 
-_GRAPH_POOL = []
+_GRAPH_POOL = {}
 
 
 def _graph_pool():
-    if not _GRAPH_POOL:
-        _GRAPH_POOL.append(torch.cuda.graph_pool_handle())
-    return _GRAPH_POOL[0]
+    """process-wide (per device) memory pool shared by every solver capture.  torch only lets a capture join an
+    existing pool while at least one live graph still references it (otherwise capture_begin trips
+    'use_count > 0' in the caching allocator -- seen when one solver's graph had been freed before the next solver
+    captured), so a tiny ANCHOR graph captured once per device owns the pool for the life of the process."""
+    dev = torch.cuda.current_device()
+    hit = _GRAPH_POOL.get(dev)
+    if hit is None:
+        torch.zeros(16, device="cuda")                   # load the fill kernel outside any capture
+        g = torch.cuda.CUDAGraph()
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            g.capture_begin(capture_error_mode="thread_local")
+            try:
+                keep = torch.zeros(16, device="cuda")    # one allocation + one kernel node: the graph is not empty
+            finally:
+                g.capture_end()
+        main.wait_stream(side)
+        hit = _GRAPH_POOL[dev] = (g.pool(), g, keep)
+    return hit[0]
 
 
 def _reset_capture_state():

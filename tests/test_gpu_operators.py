@@ -319,6 +319,30 @@ def test_cgls_config3_single_block_fp32(pm):
     assert np.linalg.norm(host(xinv.asarray()) - xt) / np.linalg.norm(xt) < 1e-5
 
 
+def test_cgls_graph_capture_survives_solver_turnover(pm):
+    """every solver captures its iteration into the process-wide graph pool: a capture must still succeed after the
+    previous solver (and its graph) has been freed (regression: torch asserts 'use_count > 0' when a capture joins a
+    pool no live graph references), and torch's RNG must stay usable afterwards"""
+    import gc
+    from pylops_mpi_b200.optimization.cls_basic import CGLS
+    n = 256
+    A = (np.random.default_rng(3).standard_normal((n, n)) / 16 + 2 * np.eye(n)).astype(np.float32)
+    xt = np.random.default_rng(4).standard_normal(n).astype(np.float32)
+    Op = pm.MPIBlockDiag([pm.MatrixMult(A)])
+    y = Op @ pm.DistributedArray.to_dist(xt)
+    for _ in range(3):
+        solver = CGLS(Op)
+        x = solver.setup(y=y, x0=pm.DistributedArray.to_dist(np.zeros(n, np.float32)), niter=20, damp=0.0, tol=0.0)
+        x = solver.run(x, 20)
+        solver.finalize()
+        assert solver.graph_error is None, solver.graph_error
+        assert solver.graph_replays >= 18
+        assert np.linalg.norm(host(x.asarray()) - xt) / np.linalg.norm(xt) < 1e-4
+        del solver, x
+        gc.collect()
+        torch.randn(8, device="cuda")          # RNG not left in capture mode
+
+
 # ---- MPIMatrixMult bf16 -> fp32 (BASELINE config 4, reduced size) --------------------------------
 @pytest.mark.parametrize("kind", ["summa", "block"])
 @pytest.mark.parametrize("M", [1, 256])
