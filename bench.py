@@ -662,6 +662,7 @@ def run_extras(pm, L, comm, peaks, args):
                                            "ms_per_iter_steady_state": (dt2 - dt) / 400 * 1e3,
                                            "cuda_graph_replays": getattr(solver, "graph_replays", 0),
                                            "cuda_graph_capture_ms": getattr(solver, "graph_capture_ms", None),
+                                           "cuda_graph_capture_breakdown_ms": getattr(solver, "graph_capture_breakdown_ms", None),
                                            "cuda_graph_error": getattr(solver, "graph_error", None)}
     # HBM-bound GEMV (A = 1 GiB)
     A2 = torch.randn(32768, 8192, device="cuda")

@@ -125,6 +125,30 @@ class DistributedArray(DistributedMixIn):
             _lib.ctx()  # fail loudly without a CUDA device / the extension
             self._local_array = torch.empty(self._local_shape, dtype=self._tdtype, device="cuda")
 
+    @classmethod
+    def _internal(cls, global_shape, local_shapes, base_comm, tdtype, buffer=None, partition=Partition.SCATTER,
+                  axis=0, mask=None):
+        """operator temporaries: every argument is already validated and normalised (tuples of ints, resolved
+        communicator, torch dtype) -- skips the checks of ``__init__`` (a few microseconds each, three per apply)"""
+        self = object.__new__(cls)
+        self._tdtype = tdtype
+        self.dtype = _lib.numpy_dtype(tdtype)
+        self._global_shape = global_shape
+        self._base_comm = base_comm
+        self._base_comm_nccl = None
+        self._partition = partition
+        self._axis = axis
+        self._mask = mask
+        self._sub_comm = base_comm if mask is None else subcomm_split(mask, base_comm)
+        self._local_shapes = local_shapes
+        self._local_shape = local_shapes[base_comm.Get_rank()]
+        self._engine = "b200"
+        if buffer is None:
+            _lib.ctx()  # fail loudly without a CUDA device / the extension
+            buffer = torch.empty(self._local_shape, dtype=tdtype, device="cuda")
+        self._local_array = buffer
+        return self
+
     # ---- element access ------------------------------------------------------
     def __getitem__(self, index):
         return self._local_array[index]
@@ -625,10 +649,9 @@ class DistributedArray(DistributedMixIn):
         """flattened DistributedArray SHARING this array's buffer (internal: used on
         operator temporaries where the reference's ravel() copy is pure overhead)"""
         local_shapes = [(math.prod(s),) for s in self._local_shapes]
-        return DistributedArray(global_shape=math.prod(self._global_shape),
-                                base_comm=self._base_comm, local_shapes=local_shapes,
-                                mask=self._mask, partition=self._partition, dtype=self._tdtype,
-                                _buffer=self._cont().reshape(-1), _trusted=True)
+        return DistributedArray._internal((math.prod(self._global_shape),), local_shapes, self._base_comm,
+                                          self._tdtype, buffer=self._cont().reshape(-1), partition=self._partition,
+                                          mask=self._mask)
 
     def empty_like(self):
         return self._like()

@@ -160,7 +160,15 @@ def ptr(t) -> int:
     return t.data_ptr()
 
 
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_GET_DEVICE = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def stream() -> int:
+    """raw ``cudaStream_t`` of torch's current stream on the current device (hot enqueue path: the private C
+    accessors avoid building a ``torch.cuda.Stream`` object, ~6 us per launch)"""
+    if _RAW_STREAM is not None and _GET_DEVICE is not None:
+        return _RAW_STREAM(_GET_DEVICE())
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -87,30 +87,38 @@ class MPIFirstDerivative(MPILinearOperator):
     def _apply(self, x: DistributedArray, adjoint: bool) -> DistributedArray:
         xl = x.local_array
         tdt = xl.dtype
-        # complex data: the stencil has real taps -> treat as 2x wider real rows
-        real_dt = {torch.complex64: torch.float32, torch.complex128: torch.float64}.get(tdt, tdt)
-        mult = 2 if tdt.is_complex else 1
-        if real_dt not in (torch.float32, torch.float64):
-            raise TypeError(f"MPIFirstDerivative supports float32/64 and complex64/128, got {tdt}")
-        # per-partition bookkeeping is pure integer work: compute once per (partition, direction)
-        key = (tuple(x._local_shapes), x.rank, bool(adjoint))
+        # everything that depends only on (partition, dtype, direction) is pure integer work: once per key
+        key = (tuple(x._local_shapes), tdt, bool(adjoint), x.mask is None, x.rank, x.size)
         cached = self._plan_cache.get(key)
         if cached is None:
+            # complex data: the stencil has real taps -> treat as 2x wider real rows
+            real_dt = {torch.complex64: torch.float32, torch.complex128: torch.float64}.get(tdt, tdt)
+            if real_dt not in (torch.float32, torch.float64):
+                raise TypeError(f"MPIFirstDerivative supports float32/64 and complex64/128, got {tdt}")
+            mult = 2 if tdt.is_complex else 1
             rows = [s[0] for s in x._local_shapes]
             need_lo, need_hi = self._halo_need(adjoint)
             plan = halo_plan(rows, x.rank, need_lo, need_hi) if x.size > 1 else None
-            cached = self._plan_cache[key] = (rows, offsets(rows)[x.rank], need_lo, need_hi, plan)
-        rows, row0, nl, nh, plan = cached
+            ncols = int(np.prod(self.dims[1:])) * mult if len(self.dims) > 1 else mult
+            esz = 4 if real_dt is torch.float32 else 8
+            vec = 16 // esz
+            # fused peer-halo path: the choice uses rank-invariant data only (global row split, dtype, ncols)
+            peer_ok = (x.size > 1 and min(rows) >= max(need_lo, need_hi, 1) and ncols % vec == 0
+                       and ncols // vec >= 8 and 2 * ncols * esz <= x.base_comm.HALO_CAP
+                       and x.base_comm.size == x.size and x.mask is None)
+            cached = self._plan_cache[key] = (rows, offsets(rows)[x.rank], need_lo, need_hi, plan, real_dt, ncols,
+                                              _lib.code(real_dt), peer_ok, [tuple(s) for s in x._local_shapes],
+                                              tuple(x.global_shape))
+        rows, row0, nl, nh, plan, real_dt, ncols, code, peer_ok, lshapes, gshape = cached
         nloc = rows[x.rank]
-        ncols = int(np.prod(self.dims[1:])) * mult if len(self.dims) > 1 else mult
-        y = DistributedArray(global_shape=x.global_shape, base_comm=x.base_comm,
-                             local_shapes=x._local_shapes, axis=x.axis, dtype=tdt, _trusted=True)
+        y = DistributedArray._internal(gshape, lshapes, x.base_comm, tdt, axis=x.axis, mask=x.mask)
         if nloc == 0:
             return y
-        xr = torch.view_as_real(xl).reshape(nloc, ncols) if tdt.is_complex else xl.reshape(nloc, ncols)
         yl = y.local_array
-        yr = torch.view_as_real(yl).reshape(nloc, ncols) if tdt.is_complex else yl.reshape(nloc, ncols)
-        code = _lib.code(real_dt)
+        if tdt.is_complex:
+            xr, yr = torch.view_as_real(xl).reshape(nloc, ncols), torch.view_as_real(yl).reshape(nloc, ncols)
+        else:
+            xr, yr = xl.reshape(nloc, ncols), yl.reshape(nloc, ncols)
         ctx = _lib.ctx()
 
         def launch(r_begin, r_end, lo_t, lo_n, hi_t, hi_n):
@@ -122,14 +130,11 @@ class MPIFirstDerivative(MPILinearOperator):
                          r_end - r_begin, ncols, row0 + r_begin, int(adjoint), code)
 
         if x.size == 1:
-            launch(0, nloc, None, 0, None, 0)
+            self._kernel(ctx, xr.data_ptr(), yr.data_ptr(), None, 0, None, 0, nloc, ncols, row0, int(adjoint), code)
             return y
         # fused path: halo rows are pushed / awaited INSIDE the stencil kernel over NVLink peer memory (ONE launch,
-        # no NCCL, no side stream).  The choice uses rank-invariant data only (global row split, dtype, ncols).
-        esz = 4 if real_dt is torch.float32 else 8
-        vec = 16 // esz
-        if min(rows) >= max(nl, nh, 1) and ncols % vec == 0 and ncols // vec >= 8 and \
-                2 * ncols * esz <= x.base_comm.HALO_CAP and x.base_comm.size == x.size and x.mask is None:
+        # no NCCL, no side stream)
+        if peer_ok:
             halo = x.base_comm.halo
             if halo is not None:
                 if xr.data_ptr() % 16:        # never branch on a rank-local property: stage a mis-aligned view

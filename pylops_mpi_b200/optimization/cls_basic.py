@@ -12,6 +12,7 @@ Two execution modes, same numbers:
 """
 from __future__ import annotations
 
+import os
 import sys
 import time
 from typing import List, Optional, Sequence
@@ -51,6 +52,7 @@ _GRAPH_SAFE_TYPES = ("MPIBlockDiag", "MPIVStack", "MPIHStack", "MPIFirstDerivati
 
 
 _GRAPH_POOL = {}
+_CAPTURE_MODE = os.environ.get("B2_CGLS_CAPTURE_MODE", "thread_local")   # diagnostics: "global" / "relaxed"
 
 
 def _graph_pool():
@@ -440,7 +442,6 @@ class CGLS(Solver):
         iteration) and replayed; the host reads the scalar history once per block.  With tol > 0 a block is at
         most 8 iterations and is re-run from a checkpoint up to the stopping iteration, so x, cost and the
         iteration count are exactly those of the reference's per-iteration test ``kold > tol`` (cls_basic.py:436)."""
-        import os
         device = x.local_array.device
         total = niter - self.iiter
         hist = torch.zeros((total + 2, 3), dtype=torch.float64, device=device)
@@ -484,6 +485,8 @@ class CGLS(Solver):
                 try:
                     # manual capture on a side stream (torch.cuda.graph() would add a device synchronise, a
                     # gc.collect() and an empty_cache() -- milliseconds, comparable to a whole 50-iteration solve)
+                    pool = _graph_pool()
+                    t_pool = time.perf_counter()
                     g = torch.cuda.CUDAGraph()
                     main = torch.cuda.current_stream()
                     if state.get("stream") is None:
@@ -497,15 +500,20 @@ class CGLS(Solver):
                         # thread_local error mode: NCCL's helper threads keep polling CUDA while we capture
                         # (observed at 8 ranks: a "global"-mode capture was invalidated and left torch's RNG state
                         # stuck in capture mode)
-                        g.capture_begin(pool=_graph_pool(), capture_error_mode="thread_local")   # records only
+                        g.capture_begin(pool=pool, capture_error_mode=_CAPTURE_MODE)   # records only
+                        t_begin = time.perf_counter()
                         try:
                             self._body(x, hist, it_dev)
                         finally:
+                            t_body = time.perf_counter()
                             g.capture_end()
                     main.wait_stream(side)
                     state["graph"] = g
                     self.graph_replays = 0
-                    self.graph_capture_ms = (time.perf_counter() - t_cap) * 1e3
+                    t_end = time.perf_counter()
+                    self.graph_capture_ms = (t_end - t_cap) * 1e3
+                    self.graph_capture_breakdown_ms = {"pool": (t_pool - t_cap) * 1e3, "begin": (t_begin - t_pool) * 1e3,
+                                                       "body": (t_body - t_begin) * 1e3, "end": (t_end - t_body) * 1e3}
                 except Exception as exc:               # not capturable (host sync inside an operator ...): stay eager
                     state["use"] = False
                     self.graph_error = repr(exc)[:300]

@@ -66,9 +66,12 @@ def reshaped(func: Optional[Callable] = None, forward: Optional[bool] = None,
             if STRICT_PARITY and x.size > 1:
                 _strict_check(x, dst)
             buf = x._repartition_flat(dst).view(local_shapes[x.rank])
-            arr = DistributedArray(global_shape=global_shape, base_comm=x.base_comm,
-                                   local_shapes=local_shapes, axis=0, dtype=x._tdtype, _buffer=buf,
-                                   _trusted=(local_shapes is not None))
+            if local_shapes is not None and type(local_shapes[0]) is tuple and type(global_shape) is tuple:
+                arr = DistributedArray._internal(global_shape, local_shapes, x.base_comm, x._tdtype, buffer=buf)
+            else:
+                arr = DistributedArray(global_shape=global_shape, base_comm=x.base_comm,
+                                       local_shapes=local_shapes, axis=0, dtype=x._tdtype, _buffer=buf,
+                                       _trusted=(local_shapes is not None))
             y: DistributedArray = f(self, arr)
             if len(y.global_shape) > 1:
                 y = y._ravel_view()      # y is a fresh temporary: flatten without the copy of :74-75
