@@ -30,7 +30,9 @@ def launches(path):
 
 def main():
     md = ["# Round 2 -- ncu evidence\n"]
-    p = os.path.join(OUT, "fr_launches_h2.csv")
+    p = os.path.join(OUT, "fr_launches_pack1.csv")        # launch list taken after the single-pass pack kernel landed
+    if not os.path.exists(p):
+        p = os.path.join(OUT, "fr_launches_h2.csv")
     if os.path.exists(p):
         md.append("## Launch list of the MPIFredholm1 tensor-core path (config 5: 64 slices of 256 x 256 x 64 complex64)\n")
         md.append("`ncu --metrics gpu__time_duration.sum --clock-control none` over `profiles/fredholm_tc_check.py --time "
@@ -58,6 +60,14 @@ def main():
     for n in (1, 2, 4, 8):
         src = os.path.join(OUT, f"r02_bench_n{n}.json")
         if os.path.exists(src) and os.path.getsize(src) > 10:
+            try:        # a line whose CGLS section fell back to eager iterations is a diagnostic, not evidence
+                line = json.loads(open(src).read().strip().splitlines()[-1])
+                bad = (line.get("extra", {}).get("cgls_blockdiag_4096_f32_50it", {}) or {}).get("cuda_graph_error")
+            except Exception:
+                bad = "unreadable"
+            if bad:
+                print(f"NOT copying {src}: {bad}")
+                continue
             shutil.copy(src, os.path.join(ROOT, "profiles", f"r02_bench_n{n}.json"))
     for name in ("r02_multi2.log", "r02_multi8.log", "r02_pytest_gpu.log"):
         src = os.path.join(OUT, name)

@@ -61,6 +61,9 @@ def allreduce_(comm: Comm, buf: torch.Tensor, op: str = SUM) -> torch.Tensor:
     return buf
 
 
+_COUNTS_CACHE = {}      # counts tuple -> (ctypes size_t array, max count): hot enqueue path of the small gathers
+
+
 def allgatherv(comm: Comm, send: torch.Tensor, counts: Sequence[int],
                out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """concatenation of every rank's flat ``send`` (counts[r] elements from rank r);
@@ -72,8 +75,14 @@ def allgatherv(comm: Comm, send: torch.Tensor, counts: Sequence[int],
         out.view(-1)[:total].copy_(send.reshape(-1))
         return out
     _flat(send)
-    arr = (C.c_size_t * comm.size)(*[int(c) for c in counts])
-    if max(int(c) for c in counts) * send.element_size() <= _PEER_VEC_MAX:
+    key = tuple(counts)
+    hit = _COUNTS_CACHE.get(key)
+    if hit is None:
+        if len(_COUNTS_CACHE) > 256:
+            _COUNTS_CACHE.clear()
+        hit = _COUNTS_CACHE[key] = ((C.c_size_t * len(key))(*[int(c) for c in key]), max(int(c) for c in key))
+    arr, cmax = hit
+    if cmax * send.element_size() <= _PEER_VEC_MAX:
         # latency regime: one-shot all-gather over peer memory (rank-invariant choice: counts and dtype only)
         pv = comm.peer_vec
         if pv is not None:

@@ -444,9 +444,8 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
         bkX = self._w * self._px
         rows_in, full_in = (self._bn, self.N) if adjoint else (bkX, self.K)
         rows_out, full_out = (bkX, self.K) if adjoint else (self._bn, self.N)
-        y = DistributedArray(global_shape=(full_out * self.M), mask=x.mask,
-                             local_shapes=self._tile_sizes(rows_out, full_out), partition=Partition.SCATTER,
-                             dtype=xdt, base_comm=x.base_comm, _trusted=True)
+        y = DistributedArray._internal((full_out * self.M,), self._tile_shapes(rows_out, full_out), x.base_comm, xdt,
+                                       mask=x.mask)
         x_block, _, local_m = self._padded_block(x, rows_in, full_in, xdt)
         if self._A_row.dtype is torch.bfloat16 and self._bm > 1:
             x_block = _cast_bf16(x_block)                 # halves the allgather payload
@@ -511,6 +510,14 @@ class _MPISummaMatrixMult(DistributedMixIn, MPILinearOperator):
             ri, ci = divmod(r, self._Pc)
             sizes.append(self._extent(rows_blk, rows_full, ri, self._Pr) * self._extent(self._bm, self.M, ci, self._Pc))
         return sizes
+
+    def _tile_shapes(self, rows_blk: int, rows_full: int):
+        """``_tile_sizes`` as a list of 1-tuples (the normalised form ``DistributedArray._internal`` takes)"""
+        cache = self.__dict__.setdefault("_tile_shapes_cache", {})
+        hit = cache.get((rows_blk, rows_full))
+        if hit is None:
+            hit = cache[(rows_blk, rows_full)] = [(int(n),) for n in self._tile_sizes(rows_blk, rows_full)]
+        return hit
 
     def _padded_block(self, x: DistributedArray, rows_blk: int, rows_full: int, xdt):
         local_r = self._extent(rows_blk, rows_full, self._row_id, self._Pr)
