@@ -10,6 +10,7 @@
 //  * op = T/H: one lane per 16-byte column vector, warps stride over the rows of a
 //            row chunk, CTA-level smem fold, chunk partials folded in chunk order
 //            by the last CTA of each column tile (deterministic, no atomics on y).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -171,6 +172,89 @@ gemv_n_kernel(const TA* __restrict__ A, size_t lda, size_t m, size_t n,
 }
 
 
+// Long rows (>= 32 KB): with one warp per row a warp streams its whole row alone, so the kernel ends with a long
+// tail in which the last few hundred warps run latency-bound (measured on 32768-column bf16 panels: a fixed ~40 us
+// on top of bytes / bandwidth -- 0.94 of the HBM peak at 32768 rows, 0.84 at 16384, ~0.65 at 8192).  Here the 8 warps
+// of a CTA sweep R rows TOGETHER, each warp taking every 8th 512-byte piece of all R rows: 2 R independent 16-byte
+// loads per lane in flight, every x vector loaded once per R rows, work per CTA R rows instead of 8 -- a shorter,
+// steeper tail.  Partial sums meet in shared memory and are added in warp order (deterministic).
+constexpr int GS_WARPS = 8;
+template <typename TA, int R>
+__global__ void __launch_bounds__(GS_WARPS * 32)
+gemv_n_split_kernel(const TA* __restrict__ A, size_t lda, size_t m, size_t n,
+                    const typename ElemTraits<TA>::X* __restrict__ x,
+                    typename ElemTraits<TA>::X* __restrict__ y) {
+  using Tr = ElemTraits<TA>;
+  using Acc = typename Tr::Acc;
+  constexpr int V = Tr::V;
+  constexpr size_t STEP = GS_WARPS * 32;
+  __shared__ Acc part[GS_WARPS][R];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t row0 = (size_t)blockIdx.x * R;
+  const TA* a[R];
+  Acc acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const size_t row = row0 + r < m ? row0 + r : m - 1;     // rows past the end re-read the last row; never stored
+    a[r] = A + row * lda;
+    acc[r] = Tr::zero();
+  }
+  const size_t nvec = n / V;
+  size_t v = (size_t)warp * 32 + lane;
+  for (; v + STEP < nvec; v += 2 * STEP) {
+    AVec<TA> a0[R], a1[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) a0[r] = load_a(a[r] + v * V);
+#pragma unroll
+    for (int r = 0; r < R; ++r) a1[r] = load_a(a[r] + (v + STEP) * V);
+    const XVec<TA> x0 = load_x<TA>(x + v * V), x1 = load_x<TA>(x + (v + STEP) * V);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) Tr::fma_(acc[r], a0[r].v[e], x0.v[e], false);
+#pragma unroll
+      for (int e = 0; e < V; ++e) Tr::fma_(acc[r], a1[r].v[e], x1.v[e], false);
+    }
+  }
+  for (; v < nvec; v += STEP) {
+    const XVec<TA> x0 = load_x<TA>(x + v * V);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const AVec<TA> a0 = load_a(a[r] + v * V);
+#pragma unroll
+      for (int e = 0; e < V; ++e) Tr::fma_(acc[r], a0.v[e], x0.v[e], false);
+    }
+  }
+  if (warp == 0)
+    for (size_t jj = nvec * V + lane; jj < n; jj += 32) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) Tr::fma_(acc[r], a[r][jj], x[jj], false);
+    }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    Acc s = acc[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s = Tr::add(s, shfl_xor_t(s, o));
+    if (lane == 0) part[warp][r] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < R && row0 + threadIdx.x < m) {
+    Acc s = part[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < GS_WARPS; ++w) s = Tr::add(s, part[w][threadIdx.x]);
+    y[row0 + threadIdx.x] = s;
+  }
+}
+
+inline bool gemv_split_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("B2_GEMV_SPLIT");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 // -------------------------------------------------------------------------
 // op = T / H : y_j = sum_i op(A_ij) x_i
 // grid = (column tiles, row chunks); CTA = 8 warps; lane <-> 16-byte column vector
@@ -281,6 +365,13 @@ int launch_gemv(b2_ctx* ctx, const void* A, size_t lda, size_t m, size_t n, cons
   if (op == B2_OP_N) {
     if (m == 0) return B2_OK;
     unsigned grid = (unsigned)((m + GN_WARPS - 1) / GN_WARPS);
+    if (vec && b2_aligned16(x) && n * sizeof(TA) >= 32768 && gemv_split_enabled()) {
+      constexpr int R = 4;
+      gemv_n_split_kernel<TA, R><<<(unsigned)((m + R - 1) / R), GS_WARPS * 32, 0, st>>>((const TA*)A, lda, m, n, (const X*)x,
+                                                                                        (X*)y);
+      B2_LAUNCH_CHECK();
+      return B2_OK;
+    }
     if (vec && b2_aligned16(x) && n >= (size_t)V)
       gemv_n_kernel<TA, true><<<grid, GN_WARPS * 32, 0, st>>>((const TA*)A, lda, m, n, (const X*)x, (X*)y);
     else

@@ -270,6 +270,40 @@ def test_gemv_all_ops(L, dt, m, n):
         np.testing.assert_allclose(yd.cpu().numpy(), ref, rtol=tol, atol=tol * scale)
 
 
+@pytest.mark.parametrize("dt", list(DT))
+@pytest.mark.parametrize("m", [1, 3, 4, 9, 130])
+def test_gemv_long_rows_split_kernel(L, dt, m):
+    """rows of >= 32 KB take the row-splitting kernel (8 warps sweep 4 rows together): ragged row counts, a row
+    pitch larger than n (view of a wider matrix, scalar remainder columns) and every element type vs float64"""
+    npdt, code = DT[dt]
+    esz = np.dtype(npdt).itemsize
+    vecw = 16 // esz
+    n = 32768 // esz + 3 * 256 * vecw + 5 * vecw + (1 if vecw > 1 else 0)   # >= 32 KB, ragged in every loop of the kernel
+    lda = -(-n // vecw) * vecw + 2 * vecw                                    # pitch: multiple of 16 bytes, > n
+    rng = np.random.default_rng(m * 31 + esz)
+    A = rnd(rng, m * lda, npdt).reshape(m, lda)
+    x = rnd(rng, n, npdt)
+    Ad, xd = dev(A), dev(x)
+    yd = torch.empty(m, dtype=xd.dtype, device="cuda")
+    L.check(L.lib.b2_gemv(L.ctx(), Ad.data_ptr(), lda, m, n, xd.data_ptr(), yd.data_ptr(), 0, code, code, L.stream()))
+    A64 = A[:, :n].astype(np.complex128 if np.iscomplexobj(A) else np.float64)
+    ref = A64 @ x.astype(A64.dtype)
+    tol = 2e-5 if dt in ("f32", "c64") else 1e-12
+    scale = np.abs(A64).sum(axis=1).max() * np.abs(x).max() + 1e-30
+    np.testing.assert_allclose(yd.cpu().numpy(), ref, rtol=tol, atol=tol * scale)
+
+
+def test_gemv_bf16_long_rows(L):
+    torch.manual_seed(2)
+    for m, n in ((5, 32768), (64, 16384 + 8 * 300)):
+        A = (torch.randn(m, n, device="cuda") / 180).to(torch.bfloat16)
+        x = torch.randn(n, device="cuda")
+        y = torch.empty(m, device="cuda")
+        L.check(L.lib.b2_gemv(L.ctx(), A.data_ptr(), n, m, n, x.data_ptr(), y.data_ptr(), 0, L.BF16, L.F32, L.stream()))
+        ref = A.double() @ x.double()
+        assert torch.allclose(y.double(), ref, rtol=1e-4, atol=1e-4)
+
+
 def test_gemv_bf16(L):
     torch.manual_seed(1)
     m, n = 1024, 2048
