@@ -733,3 +733,9 @@ def test_axis_norms_on_kernels(pm, shape, part_axis, norm_axis, dtype):
             got = host(A.norm(ord_, norm_axis))
             ref = np.linalg.norm(a.astype(np.complex128 if np.iscomplexobj(a) else np.float64), ord=ord_, axis=norm_axis)
             np.testing.assert_allclose(got, ref, rtol=1e-5 if dtype == np.float32 else 1e-12)
+
+
+def test_graft_entry_smoke(pm):
+    """the driver's smoke() entry point (config-1 KAT / adjoint / cgls + one BlockDiag block vs the oracle)"""
+    import __graft_entry__ as g
+    g.smoke()
