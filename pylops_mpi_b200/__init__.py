@@ -13,8 +13,9 @@ from .basicoperators import *  # noqa: F401,F403
 from .signalprocessing import *  # noqa: F401,F403
 from . import waveeqprocessing  # noqa: F401
 from .waveeqprocessing import MPIMDC  # noqa: F401
-from .StackedArray import (StackedDistributedArray, MPIStackedLinearOperator, MPIStackedBlockDiag,  # noqa: F401
-                           MPIStackedVStack, MPIGradient)
+from .StackedArray import StackedDistributedArray  # noqa: F401
+from .StackedLinearOperator import MPIStackedLinearOperator  # noqa: F401
+from .basicoperators import MPIStackedBlockDiag, MPIStackedVStack, MPIGradient  # noqa: F401
 from .optimization.basic import cg, cgls  # noqa: F401
 from .optimization.cls_basic import CG, CGLS  # noqa: F401
 from .optimization.sparsity import ista, fista  # noqa: F401

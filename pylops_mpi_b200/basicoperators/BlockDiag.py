@@ -12,6 +12,8 @@ from ..comm import COMM_WORLD, resolve
 from ..DistributedArray import DistributedArray
 from ..LinearOperator import MPILinearOperator, _get_dtype
 from ..local import apply_into
+from ..StackedArray import StackedDistributedArray
+from ..StackedLinearOperator import MPIStackedLinearOperator
 from ..utils.decorators import reshaped
 
 
@@ -60,3 +62,19 @@ class MPIBlockDiag(MPILinearOperator):
                              _trusted=True)
         _apply_ops(self.ops, x.local_array, self.nnops, y.local_array, self.mmops, True)
         return y
+
+
+class MPIStackedBlockDiag(MPIStackedLinearOperator):
+    """BlockDiag.py:146-204: operator i acts on stacked component i."""
+
+    def __init__(self, ops: Sequence[MPILinearOperator], base_comm=COMM_WORLD, dtype=None):
+        self.ops = ops
+        dtype = _get_dtype(self.ops) if dtype is None else np.dtype(dtype)
+        shape = (int(sum(op.shape[0] for op in ops)), int(sum(op.shape[1] for op in ops)))
+        super().__init__(shape=shape, dtype=dtype, base_comm=base_comm)
+
+    def _matvec(self, x: StackedDistributedArray) -> StackedDistributedArray:
+        return StackedDistributedArray([oper.matvec(xx) for xx, oper in zip(x.distarrays, self.ops)], self.base_comm)
+
+    def _rmatvec(self, x: StackedDistributedArray) -> StackedDistributedArray:
+        return StackedDistributedArray([oper.rmatvec(xx) for xx, oper in zip(x.distarrays, self.ops)], self.base_comm)

@@ -13,6 +13,8 @@ from ..Distributed import allreduce_
 from ..DistributedArray import DistributedArray, Partition
 from ..LinearOperator import MPILinearOperator, _get_dtype
 from ..local import apply_into
+from ..StackedArray import StackedDistributedArray
+from ..StackedLinearOperator import MPIStackedLinearOperator
 from ..utils.decorators import reshaped
 
 
@@ -66,4 +68,25 @@ class MPIVStack(MPILinearOperator):
         if len(self.ops) == 0:
             acc.zero_()
         allreduce_(x.base_comm, acc, SUM)
+        return y
+
+
+class MPIStackedVStack(MPIStackedLinearOperator):
+    """VStack.py:152-201: operators applied one after the other to the same model, outputs stacked."""
+
+    def __init__(self, ops: Sequence[MPILinearOperator], base_comm=COMM_WORLD, dtype=None):
+        self.ops = ops
+        if len(set(op.shape[1] for op in ops)) > 1:
+            raise ValueError("Operators have different number of columns")
+        shape = (int(sum(op.shape[0] for op in ops)), ops[0].shape[1])
+        dtype = _get_dtype(self.ops) if dtype is None else np.dtype(dtype)
+        super().__init__(shape=shape, dtype=dtype, base_comm=base_comm)
+
+    def _matvec(self, x: DistributedArray) -> StackedDistributedArray:
+        return StackedDistributedArray([oper.matvec(x) for oper in self.ops], self.base_comm)
+
+    def _rmatvec(self, x: StackedDistributedArray) -> DistributedArray:
+        y = self.ops[0].rmatvec(x[0])
+        for xx, oper in zip(x[1:], self.ops[1:]):
+            y += oper.rmatvec(xx)
         return y
