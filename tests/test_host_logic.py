@@ -288,3 +288,30 @@ def test_cgls_graph_whitelist_is_conservative():
     assert not _graph_safe(make("MPILinearOperator"))                       # wrapper of an arbitrary local operator
     assert not _graph_safe(make("MPIBlockDiag", ops=[make("SomeUserOperator")]))
     assert not _graph_safe(make("_SumLinearOperator", args=(make("MPIBlockDiag", ops=[blk]), make("MPIFredholm1"))))
+
+
+def test_stacked_operator_algebra_without_a_device():
+    """shape / type bookkeeping and the error behaviour of the MPIStackedLinearOperator algebra
+    (StackedLinearOperator.py:117-228, 268-293) need no device: checked with shape-only stand-in operators"""
+    import pylops_mpi_b200 as pm
+
+    class Shape:
+        def __init__(self, m, n):
+            self.shape, self.dtype = (m, n), np.dtype(np.float64)
+
+    V1, V2 = (pm.MPIStackedVStack([Shape(4, 3), Shape(5, 3)]) for _ in range(2))
+    B1, B2 = pm.MPIStackedBlockDiag([Shape(4, 3), Shape(5, 3)]), pm.MPIStackedBlockDiag([Shape(3, 3)])
+    assert V1.shape == (9, 3) and B1.shape == (9, 6)
+    with pytest.raises(ValueError, match="both operands cannot be MPIStackedVStack"):
+        V1 * V2
+    with pytest.raises(ValueError, match="different number of ops"):
+        B1 * B2
+    with pytest.raises(ValueError, match="different number of columns"):
+        pm.MPIStackedVStack([Shape(4, 3), Shape(5, 2)])
+    assert (B1.H * B1).shape == (6, 6) and (B1 + B1).shape == (9, 6) and (2 * B1).shape == (9, 6)
+    assert B1.H.shape == (6, 9) and (-B1).shape == (9, 6) and (B1.H * V1.H.H).shape == (6, 3)
+    # the classes live where the reference keeps them; the old module path still resolves
+    import pylops_mpi_b200.StackedArray as sa
+    assert sa.MPIGradient is pm.MPIGradient and sa.MPIStackedLinearOperator is pm.MPIStackedLinearOperator
+    assert pm.MPIGradient.__module__.endswith("basicoperators.Gradient")
+    assert pm.MPIStackedLinearOperator.__module__.endswith("StackedLinearOperator")
