@@ -111,7 +111,7 @@ class MPIFirstDerivative(MPILinearOperator):
                                               tuple(x.global_shape))
         rows, row0, nl, nh, plan, real_dt, ncols, code, peer_ok, lshapes, gshape = cached
         nloc = rows[x.rank]
-        y = DistributedArray._internal(gshape, lshapes, x.base_comm, tdt, axis=x.axis, mask=x.mask)
+        y = DistributedArray._internal(gshape, lshapes, x.base_comm, tdt, axis=x.axis)    # no mask, as :144-145
         if nloc == 0:
             return y
         yl = y.local_array
