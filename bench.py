@@ -532,7 +532,9 @@ def run_secondary(pm, L, comm, peaks, args):
             ms = time_loop(lambda: Sop.matvec(xs), 20, 10, comm)
             gb = 2.0 * Ng * Kg * 20 / (ms * 1e-3) / 1e9
             out["m1_32768_vec"] = {"us": ms / 20 * 1e3, "GB/s_A": gb, "GF/s": gb, "frac_hbm": gb / (size * hbm),
-                                   "layout": f"1-D row panels, grid {size}x1", "bound": "hbm (1 flop/B)"}
+                                   "host_enqueue_us": time_loop.last_enqueue_ms * 1e3,
+                                   "layout": f"1-D row panels, grid {size}x1: one-shot peer all-gather of x + row-splitting GEMV",
+                                   "bound": "hbm (1 flop/B)"}
             del Sop, xs, At1
         except Exception as exc:
             out["m1_32768_vec"] = {"error": repr(exc)}
