@@ -315,3 +315,44 @@ def test_stacked_operator_algebra_without_a_device():
     assert sa.MPIGradient is pm.MPIGradient and sa.MPIStackedLinearOperator is pm.MPIStackedLinearOperator
     assert pm.MPIGradient.__module__.endswith("basicoperators.Gradient")
     assert pm.MPIStackedLinearOperator.__module__.endswith("StackedLinearOperator")
+
+
+def test_stacked_operator_dispatch_on_host_buffers():
+    """matvec / rmatvec / adjoint / product dispatch of MPIStackedVStack and MPIStackedBlockDiag
+    (VStack.py:152-201, BlockDiag.py:146-204, StackedLinearOperator.py:230-293) with stand-in operators working on
+    host buffers: the composition glue itself never touches the device"""
+    import torch
+    import pylops_mpi_b200 as pm
+    from pylops_mpi_b200.DistributedArray import DistributedArray
+    comm = pm.get_comm_world()
+
+    def da(v):
+        t = torch.as_tensor(np.asarray(v, dtype=np.float64))
+        return DistributedArray._internal((t.numel(),), [(t.numel(),)], comm, torch.float64, buffer=t)
+
+    class Dense:
+        def __init__(self, A):
+            self.A, self.shape, self.dtype = np.asarray(A, float), np.shape(A), np.dtype(float)
+
+        def matvec(self, x):
+            return da(self.A @ x.local_array.numpy())
+
+        def rmatvec(self, x):
+            return da(self.A.T @ x.local_array.numpy())
+
+    rng = np.random.default_rng(0)
+    A1, A2 = rng.standard_normal((4, 3)), rng.standard_normal((5, 3))
+    x = da(rng.standard_normal(3))
+    y = pm.MPIStackedVStack([Dense(A1), Dense(A2)]).matvec(x)
+    assert isinstance(y, pm.StackedDistributedArray) and y.narrays == 2
+    np.testing.assert_allclose(y[0].local_array.numpy(), A1 @ x.local_array.numpy())
+    np.testing.assert_allclose(y[1].local_array.numpy(), A2 @ x.local_array.numpy())
+    B = pm.MPIStackedBlockDiag([Dense(A1), Dense(A2)])
+    xs = pm.StackedDistributedArray([da(rng.standard_normal(3)), da(rng.standard_normal(3))])
+    yb = B.matvec(xs)
+    zb = B.H.matvec(yb)
+    np.testing.assert_allclose(zb[1].local_array.numpy(), A2.T @ (A2 @ xs[1].local_array.numpy()))
+    zp = (B.H * B).matvec(xs)
+    np.testing.assert_allclose(zp[0].local_array.numpy(), A1.T @ (A1 @ xs[0].local_array.numpy()))
+    with pytest.raises(ValueError):
+        B.matvec(x)          # a plain 3-vector is not the 6-element stacked model
