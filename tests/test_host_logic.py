@@ -356,3 +356,17 @@ def test_stacked_operator_dispatch_on_host_buffers():
     np.testing.assert_allclose(zp[0].local_array.numpy(), A1.T @ (A1 @ xs[0].local_array.numpy()))
     with pytest.raises(ValueError):
         B.matvec(x)          # a plain 3-vector is not the 6-element stacked model
+
+
+def test_gradient_constructor_bookkeeping(monkeypatch):
+    """MPIGradient (Gradient.py:21-119) = distributed first derivative along axis 0 + one rank-local BlockDiag per
+    other axis: shapes, sampling broadcast and operator types (constructor only; the device context is stubbed)"""
+    import pylops_mpi_b200 as pm
+    from pylops_mpi_b200 import _lib
+    monkeypatch.setattr(_lib, "ctx", lambda device=None: None)
+    G = pm.MPIGradient((8, 5, 3), sampling=(1.0, 0.5, 2.0), kind="centered", dtype="float64")
+    assert G.shape == (3 * 120, 120) and G.dtype == np.float64
+    assert [type(op).__name__ for op in G.ops] == ["MPIFirstDerivative", "MPIBlockDiag", "MPIBlockDiag"]
+    G1 = pm.MPIGradient((8, 5), sampling=2.0, kind="forward", edge=True)
+    assert G1.shape == (80, 40) and G1.sampling == (2.0, 2.0) and G1.edge and G1.kind == "forward"
+    assert isinstance(G1, pm.MPIStackedVStack) and isinstance(G1, pm.MPIStackedLinearOperator)
